@@ -1,0 +1,103 @@
+/*
+ * rtf_b200.h — C-ABI of librtf_b200.so: the B200 (sm_100a) kernels behind the
+ * recommend-tf2.0 embedding + feature-interaction layers.
+ *
+ * The reference (littlemesie/recommend-tf2.0) has no native interface: its
+ * boundary is the Keras Layer protocol.  Each entry point below
+ * names the reference call site whose stock-TensorFlow op sequence it replaces
+ * (paths relative to the reference root).  The reference-side binding (ctypes
+ * from the Python layer classes; a tf.load_op_library REGISTER_OP shim over the
+ * same symbols) is shown in INTEGRATION.md.
+ *
+ * Conventions
+ *  - every pointer named d_* / tables / grad / out is a DEVICE pointer unless
+ *    the comment says HOST; small descriptor arrays (tables[], rows[], dims[])
+ *    are HOST arrays that are copied into kernel parameters;
+ *  - the caller owns every buffer, including workspaces (size query functions);
+ *    the library never allocates or frees device memory and keeps no global
+ *    mutable state; all work is enqueued on `stream` (a cudaStream_t) and no
+ *    entry point synchronises the device;
+ *  - return value: 0 = ok, negative = argument error (RTF_E_*), positive =
+ *    cudaError_t from the launch;
+ *  - out-of-range ids are never dereferenced: the row reads as zeros and bit 0
+ *    of *d_err is set (TF CPU raises InvalidArgument; the Python layer raises
+ *    when it reads the flag).
+ */
+#ifndef RTF_B200_H
+#define RTF_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define RTF_MAX_FIELDS 64 /* lookup slots per launch (the library chunks above it) */
+
+#define RTF_E_ARG (-1)       /* null pointer / non-positive size */
+#define RTF_E_ALIGN (-2)     /* pointer or stride not aligned for the vector path */
+#define RTF_E_RANGE (-3)     /* size out of supported range */
+#define RTF_E_WORKSPACE (-4) /* workspace too small */
+
+enum { RTF_POOL_NONE = 0, RTF_POOL_SUM = 1, RTF_POOL_MEAN = 2 };
+enum { RTF_OPT_NONE = 0, RTF_OPT_SGD = 1, RTF_OPT_ADAGRAD = 2, RTF_OPT_ADAM = 3 };
+
+/* Sparse row-wise optimizer applied in place to the rows touched by a batch.
+ * Keras semantics: Adam  m<-b1 m+(1-b1)g, v<-b2 v+(1-b2)g^2,
+ * w <- w - lr_t * m/(sqrt(v)+eps), lr_t = lr*sqrt(1-b2^t)/(1-b1^t) (host passes
+ * lr_t in `lr`); Adagrad acc<-acc+g^2, w<-w-lr*g/(sqrt(acc)+eps); SGD w<-w-lr*g.
+ * l2 > 0 adds the regulariser gradient 2*l2*w of the touched row to g first. */
+typedef struct rtf_opt {
+  int32_t kind; /* RTF_OPT_* */
+  float lr;
+  float beta1;
+  float beta2;
+  float eps;
+  float l2;
+} rtf_opt;
+
+/* library / build identification: returns the sm arch the kernels were built for (100) */
+int rtf_version(int* sm_arch);
+
+/* ---- K1: fused multi-table gather (+ sum/mean pooling over L) -----------------
+ * replaces: tf.concat([embed_i(sparse[:, i]) ...], -1)   src/ctr/dlrm/model.py:45-46
+ *           (+ deep_fm/model.py:53-54, autoint/model.py:46-47, din/model.py:62-74,
+ *            match/sasrec/model.py:75-79) and reduce_sum(axis=1) src/match/fm/model.py:73,77
+ * out[b, l, off_f + d] = W_f[ids[b,f,l], d]           (pool NONE; out is (B, L, sumD))
+ * out[b, off_f + d]    = sum_l / mean_l W_f[ids[b,f,l], d]   (ascending l, fp32)
+ * tables/rows/dims: HOST arrays of n_fields entries (a table may repeat).
+ * ids: int32 or int64 device array addressed ids[b*sb + f*sf + l*sl].
+ * out_sb: elements between consecutive samples of out (>= L*sumD or sumD). */
+int rtf_embed_fwd(const float* const* tables, const int64_t* rows, const int32_t* dims,
+                  int n_fields, const void* d_ids, int ids_i64, int64_t B, int L,
+                  int64_t ids_sb, int64_t ids_sf, int64_t ids_sl, int pool, float* d_out,
+                  int64_t out_sb, int32_t* d_err, void* stream);
+
+/* ---- K2: deterministic embedding backward + in-place sparse optimizer ---------
+ * replaces: IndexedSlices -> UnsortedSegmentSum -> ResourceApplyAdam implied by
+ *           model.compile(optimizer=Adam) src/ctr/fm/train.py:49-50
+ * sort (table,id) keys (stable LSD radix, payload = lookup position), find the
+ * segments, sum each segment's gradient rows in ascending lookup position
+ * (chunks of RTF_SEG_CHUNK rows, chunk partials combined in order), then apply
+ * `opt` to the touched rows.  Lookup position p = (b*L + l)*n_fields + f.
+ * field_table[f] (HOST) maps a field to one of n_tables distinct tables;
+ * weights/state1/state2/rows/dims are HOST arrays of n_tables entries
+ * (state1 = Adam m or Adagrad acc, state2 = Adam v; unused may be NULL).
+ * d_grad has the layout of K1's out.  Optional outputs for inspection/tests:
+ * d_uniq_key[n] (table*2^row_bits + row, ascending), d_uniq_grad[n, dim_max]
+ * (the summed rows), d_num_uniq[1], and *row_bits_out (HOST). */
+#define RTF_SEG_CHUNK 64
+int rtf_embed_bwd_workspace(int64_t n_lookups, int dim_max, size_t* bytes);
+int rtf_embed_bwd(float* const* weights, float* const* state1, float* const* state2,
+                  const int64_t* rows, const int32_t* dims, int n_tables,
+                  const int32_t* field_table, int n_fields, const void* d_ids, int ids_i64,
+                  int64_t B, int L, int64_t ids_sb, int64_t ids_sf, int64_t ids_sl, int pool,
+                  const float* d_grad, int64_t grad_sb, const rtf_opt* opt,
+                  uint32_t* d_uniq_key, float* d_uniq_grad, int32_t* d_num_uniq,
+                  int* row_bits_out, void* d_workspace, size_t workspace_bytes, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* RTF_B200_H */

@@ -1,0 +1,11 @@
+"""recommend-tf2.0_b200 — B200 (sm_100a) kernels behind the recommend-tf2.0 embedding and
+feature-interaction layers.  Import as `recommend_tf2_b200` (see ../recommend_tf2_b200.py).
+
+Nothing here computes on the CPU: every op dispatches to librtf_b200.so and raises if the
+library or a CUDA device is missing."""
+from . import _lib
+from ._lib import RtfError, build, lib
+from .embedding import EmbeddingTables, SparseOptimizer, embed_bwd, embed_fwd
+
+__all__ = ["RtfError", "build", "lib", "EmbeddingTables", "SparseOptimizer", "embed_fwd",
+           "embed_bwd"]

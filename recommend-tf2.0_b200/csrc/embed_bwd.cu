@@ -1,0 +1,753 @@
+// K2 — deterministic embedding backward with in-place sparse optimizers.
+//
+// Replaces IndexedSlices -> UnsortedSegmentSum (atomics, non-deterministic) -> dense
+// ResourceApplyAdam that the reference's model.compile(optimizer=Adam) lowers to
+// (src/ctr/fm/train.py:49-50).
+//
+// Pipeline, all on the caller's stream, no host sync:
+//   1. keys[p] = table(field(p)) << row_bits | id      (p = lookup position, ascending b,l,f)
+//   2. stable LSD radix sort of (key, p), 8 bits per pass over the significant bits only
+//   3. head flags + scan -> segment starts (one segment per touched row)
+//   4. segment reduce: one lane-group per segment adds its gradient rows in ascending p.
+//      Segments longer than RTF_SEG_CHUNK are split into fixed chunks whose partial sums
+//      are combined in chunk order — the summation tree depends only on the segment, so
+//      results are reproducible bit for bit — then the optimizer updates the row in place.
+// HBM-bound: per lookup one gradient row read, per touched row W/m/v read+write.
+#include "rtf_common.cuh"
+
+namespace rtf {
+
+// ------------------------------------------------------------------ parameters
+struct BwdParams {
+  float* w[RTF_MAX_FIELDS];
+  float* s1[RTF_MAX_FIELDS];
+  float* s2[RTF_MAX_FIELDS];
+  long long rows[RTF_MAX_FIELDS];
+  int dim[RTF_MAX_FIELDS];        // per table
+  int field_table[RTF_MAX_FIELDS];
+  int field_off[RTF_MAX_FIELDS];  // column offset of a field in one grad row
+  int n_tables, n_fields, sumD, row_bits, L, pool;
+  long long grad_sb;
+  rtf_opt opt;
+};
+
+// ------------------------------------------------------------------ 1. keys
+template <typename IdT>
+__global__ void __launch_bounds__(256)
+make_keys(const __grid_constant__ BwdParams P, const IdT* __restrict__ ids, long long n,
+          long long sb, long long sf, long long sl, uint32_t* __restrict__ keys) {
+  const long long p = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (p >= n) return;
+  const int F = P.n_fields;
+  const long long LF = (long long)P.L * F;
+  const long long b = p / LF;
+  const int r = (int)(p - b * LF);
+  const int l = r / F;
+  const int f = r - l * F;
+  const int t = P.field_table[f];
+  const long long id = (long long)__ldg(ids + b * sb + (long long)f * sf + (long long)l * sl);
+  uint32_t key;
+  if (id < 0 || id >= P.rows[t])
+    key = (uint32_t)P.n_tables << P.row_bits;  // sentinel "table": sorts last, never applied
+  else
+    key = ((uint32_t)t << P.row_bits) | (uint32_t)id;
+  keys[p] = key;
+}
+
+// ------------------------------------------------------------------ scan utility
+// exclusive scan of f(i), i in [0,n): tile sums -> scan of tile sums -> apply
+constexpr int SCAN_THREADS = 256;
+constexpr int SCAN_ITEMS = 8;
+constexpr int SCAN_TILE = SCAN_THREADS * SCAN_ITEMS;
+
+__device__ __forceinline__ uint32_t block_exclusive_scan(uint32_t v, uint32_t* total) {
+  // 256 threads; returns exclusive prefix of v across the block
+  __shared__ uint32_t warp_tot[SCAN_THREADS / 32];
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+  uint32_t inc = v;
+#pragma unroll
+  for (int o = 1; o < 32; o <<= 1) {
+    uint32_t y = __shfl_up_sync(0xffffffffu, inc, o);
+    if (lane >= o) inc += y;
+  }
+  if (lane == 31) warp_tot[wid] = inc;
+  __syncthreads();
+  uint32_t base = 0, tot = 0;
+#pragma unroll
+  for (int w = 0; w < SCAN_THREADS / 32; ++w) {
+    const uint32_t t = warp_tot[w];
+    if (w < wid) base += t;
+    tot += t;
+  }
+  __syncthreads();
+  *total = tot;
+  return base + inc - v;
+}
+
+template <typename In>
+__global__ void __launch_bounds__(SCAN_THREADS)
+scan_tile_reduce(In in, long long n, uint32_t* __restrict__ tile_sums) {
+  const long long base = (long long)blockIdx.x * SCAN_TILE + (long long)threadIdx.x * SCAN_ITEMS;
+  uint32_t s = 0;
+#pragma unroll
+  for (int k = 0; k < SCAN_ITEMS; ++k)
+    if (base + k < n) s += in(base + k);
+  uint32_t tot;
+  block_exclusive_scan(s, &tot);
+  if (threadIdx.x == 0) tile_sums[blockIdx.x] = tot;
+}
+
+__global__ void __launch_bounds__(1024) scan_tile_sums(uint32_t* __restrict__ tile_sums, int nt) {
+  __shared__ uint32_t wsum[32];
+  __shared__ uint32_t carry_s;
+  if (threadIdx.x == 0) carry_s = 0;
+  __syncthreads();
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+  for (int base = 0; base < nt; base += 1024) {
+    const int i = base + threadIdx.x;
+    const uint32_t v = i < nt ? tile_sums[i] : 0;
+    uint32_t inc = v;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      uint32_t y = __shfl_up_sync(0xffffffffu, inc, o);
+      if (lane >= o) inc += y;
+    }
+    if (lane == 31) wsum[wid] = inc;
+    __syncthreads();
+    if (wid == 0) {
+      uint32_t w = wsum[lane], winc = w;
+#pragma unroll
+      for (int o = 1; o < 32; o <<= 1) {
+        uint32_t y = __shfl_up_sync(0xffffffffu, winc, o);
+        if (lane >= o) winc += y;
+      }
+      wsum[lane] = winc - w;  // exclusive warp offsets
+    }
+    __syncthreads();
+    const uint32_t carry = carry_s;
+    const uint32_t excl = carry + wsum[wid] + inc - v;
+    if (i < nt) tile_sums[i] = excl;
+    __syncthreads();
+    if (threadIdx.x == 1023) carry_s = excl + v;
+    __syncthreads();
+  }
+}
+
+template <typename In, typename Out>
+__global__ void __launch_bounds__(SCAN_THREADS)
+scan_tile_apply(In in, Out out, long long n, const uint32_t* __restrict__ tile_sums) {
+  const long long base = (long long)blockIdx.x * SCAN_TILE + (long long)threadIdx.x * SCAN_ITEMS;
+  uint32_t v[SCAN_ITEMS];
+  uint32_t s = 0;
+#pragma unroll
+  for (int k = 0; k < SCAN_ITEMS; ++k) {
+    v[k] = base + k < n ? in(base + k) : 0;
+    s += v[k];
+  }
+  uint32_t tot;
+  uint32_t ex = block_exclusive_scan(s, &tot) + tile_sums[blockIdx.x];
+#pragma unroll
+  for (int k = 0; k < SCAN_ITEMS; ++k) {
+    if (base + k < n) out(base + k, ex, v[k]);
+    ex += v[k];
+  }
+}
+
+struct InArray {
+  const uint32_t* a;
+  __device__ uint32_t operator()(long long i) const { return a[i]; }
+};
+struct OutArray {
+  uint32_t* a;
+  __device__ void operator()(long long i, uint32_t ex, uint32_t) const { a[i] = ex; }
+};
+struct InHeadFlag {  // 1 where a new (table,row) segment starts in the sorted keys
+  const uint32_t* keys;
+  __device__ uint32_t operator()(long long i) const {
+    return (i == 0 || keys[i] != keys[i - 1]) ? 1u : 0u;
+  }
+};
+struct OutSegments {
+  const uint32_t* keys;
+  uint32_t* seg_start;  // [n+1]
+  int32_t* counters;    // [0] = n_seg, [1] = n_valid_seg
+  int32_t* d_num_uniq;  // optional
+  long long n;
+  uint32_t sentinel_table;
+  int row_bits;
+  __device__ void operator()(long long i, uint32_t ex, uint32_t flag) const {
+    if (flag) seg_start[ex] = (uint32_t)i;
+    if (i == n - 1) {
+      const uint32_t nseg = ex + flag;
+      seg_start[nseg] = (uint32_t)n;
+      const int valid = (int)nseg - ((keys[i] >> row_bits) == sentinel_table ? 1 : 0);
+      counters[0] = (int)nseg;
+      counters[1] = valid;
+      if (d_num_uniq) *d_num_uniq = valid;
+    }
+  }
+};
+
+template <typename In, typename Out>
+static int exclusive_scan(In in, Out out, long long n, uint32_t* tile_sums, cudaStream_t st) {
+  const long long nt = (n + SCAN_TILE - 1) / SCAN_TILE;
+  scan_tile_reduce<In><<<(unsigned)nt, SCAN_THREADS, 0, st>>>(in, n, tile_sums);
+  scan_tile_sums<<<1, 1024, 0, st>>>(tile_sums, (int)nt);
+  scan_tile_apply<In, Out><<<(unsigned)nt, SCAN_THREADS, 0, st>>>(in, out, n, tile_sums);
+  RTF_CHECK_LAUNCH();
+  return 0;
+}
+
+// ------------------------------------------------------------------ 2. radix sort
+constexpr int SORT_THREADS = 256;
+constexpr int SORT_WARPS = SORT_THREADS / 32;
+constexpr int SORT_ITEMS = 16;
+constexpr int SORT_TILE = SORT_THREADS * SORT_ITEMS;  // 4096 keys per CTA; a warp owns 512 contiguous
+
+__global__ void __launch_bounds__(SORT_THREADS)
+sort_hist(const uint32_t* __restrict__ keys, long long n, int shift, uint32_t* __restrict__ hist,
+          int nblk) {
+  __shared__ uint32_t sh[256];
+  sh[threadIdx.x] = 0;
+  __syncthreads();
+  const long long base = (long long)blockIdx.x * SORT_TILE;
+#pragma unroll
+  for (int r = 0; r < SORT_ITEMS; ++r) {
+    const long long i = base + r * SORT_THREADS + threadIdx.x;
+    if (i < n) atomicAdd(&sh[(keys[i] >> shift) & 255u], 1u);
+  }
+  __syncthreads();
+  hist[(long long)threadIdx.x * nblk + blockIdx.x] = sh[threadIdx.x];  // digit-major
+}
+
+__global__ void __launch_bounds__(SORT_THREADS)
+sort_scatter(const uint32_t* __restrict__ keys_in, const uint32_t* __restrict__ vals_in,
+             uint32_t* __restrict__ keys_out, uint32_t* __restrict__ vals_out, long long n,
+             int shift, const uint32_t* __restrict__ hist_scanned, int nblk, int iota_vals) {
+  __shared__ uint32_t whist[SORT_WARPS][256];
+  for (int i = threadIdx.x; i < SORT_WARPS * 256; i += SORT_THREADS) (&whist[0][0])[i] = 0;
+  __syncthreads();
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+  const uint32_t lt_mask = (1u << lane) - 1u;
+  const long long wbase = (long long)blockIdx.x * SORT_TILE + (long long)wid * (32 * SORT_ITEMS);
+  uint32_t k[SORT_ITEMS], v[SORT_ITEMS], rank[SORT_ITEMS];
+#pragma unroll
+  for (int r = 0; r < SORT_ITEMS; ++r) {
+    const long long i = wbase + r * 32 + lane;
+    const bool valid = i < n;
+    k[r] = valid ? keys_in[i] : 0xffffffffu;
+    v[r] = valid ? (iota_vals ? (uint32_t)i : vals_in[i]) : 0u;
+    const uint32_t vmask = __ballot_sync(0xffffffffu, valid);
+    rank[r] = 0;
+    if (valid) {
+      const uint32_t d = (k[r] >> shift) & 255u;
+      const uint32_t m = __match_any_sync(vmask, d);
+      const uint32_t prior = whist[wid][d];
+      __syncwarp(vmask);
+      if ((m & lt_mask) == 0) whist[wid][d] = prior + __popc(m);  // lowest lane of the match set
+      __syncwarp(vmask);
+      rank[r] = prior + __popc(m & lt_mask);
+    }
+  }
+  __syncthreads();
+  {  // thread d turns per-warp counts into global bases (warps in index order => stable)
+    const int d = threadIdx.x;
+    uint32_t run = hist_scanned[(long long)d * nblk + blockIdx.x];
+#pragma unroll
+    for (int w = 0; w < SORT_WARPS; ++w) {
+      const uint32_t c = whist[w][d];
+      whist[w][d] = run;
+      run += c;
+    }
+  }
+  __syncthreads();
+#pragma unroll
+  for (int r = 0; r < SORT_ITEMS; ++r) {
+    const long long i = wbase + r * 32 + lane;
+    if (i < n) {
+      const uint32_t d = (k[r] >> shift) & 255u;
+      const uint32_t pos = whist[wid][d] + rank[r];
+      keys_out[pos] = k[r];
+      vals_out[pos] = v[r];
+    }
+  }
+}
+
+// ------------------------------------------------------------------ 4. segment reduce
+template <int VEC>
+struct Vec {
+  float v[VEC];
+};
+template <int VEC>
+__device__ __forceinline__ Vec<VEC> vload(const float* p) {
+  Vec<VEC> r;
+  if constexpr (VEC == 4) {
+    const float4 t = *reinterpret_cast<const float4*>(p);
+    r.v[0] = t.x; r.v[1] = t.y; r.v[2] = t.z; r.v[3] = t.w;
+  } else {
+    r.v[0] = *p;
+  }
+  return r;
+}
+template <int VEC>
+__device__ __forceinline__ Vec<VEC> vload_stream(const float* p) {
+  Vec<VEC> r;
+  if constexpr (VEC == 4) {
+    const float4 t = ldg_nc_f4(p);
+    r.v[0] = t.x; r.v[1] = t.y; r.v[2] = t.z; r.v[3] = t.w;
+  } else {
+    r.v[0] = __ldg(p);
+  }
+  return r;
+}
+template <int VEC>
+__device__ __forceinline__ void vstore(float* p, const Vec<VEC>& a) {
+  if constexpr (VEC == 4)
+    *reinterpret_cast<float4*>(p) = make_float4(a.v[0], a.v[1], a.v[2], a.v[3]);
+  else
+    *p = a.v[0];
+}
+
+// pointer to the gradient row of lookup position p
+__device__ __forceinline__ const float* grad_row(const BwdParams& P, const float* grad,
+                                                 uint32_t p) {
+  const int F = P.n_fields;
+  const uint32_t LF = (uint32_t)P.L * (uint32_t)F;
+  const uint32_t b = p / LF;
+  const uint32_t r = p - b * LF;
+  const uint32_t l = r / (uint32_t)F;
+  const uint32_t f = r - l * (uint32_t)F;
+  const long long lo = P.pool == RTF_POOL_NONE ? (long long)l * P.sumD : 0;
+  return grad + (long long)b * P.grad_sb + lo + P.field_off[f];
+}
+
+// acc[k] (+)= rows vals[start..end) in ascending order, U loads in flight
+template <int VEC, int G, int VPL>
+__device__ __forceinline__ void sum_rows(const BwdParams& P, const float* __restrict__ grad,
+                                         const uint32_t* __restrict__ vals, uint32_t start,
+                                         uint32_t end, int nv, int lg, float scale,
+                                         Vec<VEC> (&acc)[VPL]) {
+  constexpr int U = 4;
+  for (uint32_t j0 = start; j0 < end; j0 += U) {
+    const float* src[U];
+#pragma unroll
+    for (int u = 0; u < U; ++u) src[u] = j0 + u < end ? grad_row(P, grad, vals[j0 + u]) : nullptr;
+    Vec<VEC> x[U][VPL];
+#pragma unroll
+    for (int u = 0; u < U; ++u)
+#pragma unroll
+      for (int k = 0; k < VPL; ++k) {
+        const int vi = lg + k * G;
+        if (src[u] && vi < nv) x[u][k] = vload_stream<VEC>(src[u] + VEC * vi);
+      }
+#pragma unroll
+    for (int u = 0; u < U; ++u)
+      if (src[u]) {
+#pragma unroll
+        for (int k = 0; k < VPL; ++k) {
+          const int vi = lg + k * G;
+          if (vi < nv) {
+#pragma unroll
+            for (int e = 0; e < VEC; ++e) {
+              float g = x[u][k].v[e];
+              if (P.pool == RTF_POOL_MEAN) g = __fmul_rn(g, scale);
+              acc[k].v[e] = __fadd_rn(acc[k].v[e], g);
+            }
+          }
+        }
+      }
+  }
+}
+
+// apply the optimizer to row `row` of table t with summed gradient acc; optional copies out
+template <int VEC, int G, int VPL>
+__device__ __forceinline__ void finish_row(const BwdParams& P, uint32_t key, uint32_t seg,
+                                           int nv, int lg, Vec<VEC> (&acc)[VPL],
+                                           uint32_t* uniq_key, float* uniq_grad, int dim_max) {
+  const uint32_t t = key >> P.row_bits;
+  const long long row = (long long)(key & ((1u << P.row_bits) - 1u));
+  const int dim = P.dim[t];
+  if (uniq_key && lg == 0) uniq_key[seg] = key;
+  if (uniq_grad) {
+#pragma unroll
+    for (int k = 0; k < VPL; ++k) {
+      const int vi = lg + k * G;
+      if (vi < nv) vstore<VEC>(uniq_grad + (long long)seg * dim_max + VEC * vi, acc[k]);
+    }
+  }
+  const rtf_opt& o = P.opt;
+  if (o.kind == RTF_OPT_NONE) return;
+  float* w = P.w[t] + row * dim;
+  float* s1 = P.s1[t] ? P.s1[t] + row * dim : nullptr;
+  float* s2 = P.s2[t] ? P.s2[t] + row * dim : nullptr;
+  const float two_l2 = __fmul_rn(2.0f, o.l2);
+#pragma unroll
+  for (int k = 0; k < VPL; ++k) {
+    const int vi = lg + k * G;
+    if (vi >= nv) continue;
+    Vec<VEC> wv = vload<VEC>(w + VEC * vi);
+    Vec<VEC> a, b;
+    if (o.kind >= RTF_OPT_ADAGRAD) a = vload<VEC>(s1 + VEC * vi);
+    if (o.kind == RTF_OPT_ADAM) b = vload<VEC>(s2 + VEC * vi);
+#pragma unroll
+    for (int e = 0; e < VEC; ++e) {
+      float g = acc[k].v[e];
+      if (o.l2 > 0.f) g = __fadd_rn(g, __fmul_rn(two_l2, wv.v[e]));
+      if (o.kind == RTF_OPT_SGD) {
+        wv.v[e] = __fsub_rn(wv.v[e], __fmul_rn(o.lr, g));
+      } else if (o.kind == RTF_OPT_ADAGRAD) {
+        a.v[e] = __fadd_rn(a.v[e], __fmul_rn(g, g));
+        wv.v[e] = __fsub_rn(wv.v[e], __fdiv_rn(__fmul_rn(o.lr, g),
+                                               __fadd_rn(__fsqrt_rn(a.v[e]), o.eps)));
+      } else {  // Adam (Keras form; lr already carries the bias corrections)
+        a.v[e] = __fadd_rn(__fmul_rn(o.beta1, a.v[e]), __fmul_rn(__fsub_rn(1.0f, o.beta1), g));
+        b.v[e] = __fadd_rn(__fmul_rn(o.beta2, b.v[e]),
+                           __fmul_rn(__fsub_rn(1.0f, o.beta2), __fmul_rn(g, g)));
+        wv.v[e] = __fsub_rn(wv.v[e], __fdiv_rn(__fmul_rn(o.lr, a.v[e]),
+                                               __fadd_rn(__fsqrt_rn(b.v[e]), o.eps)));
+      }
+    }
+    vstore<VEC>(w + VEC * vi, wv);
+    if (o.kind >= RTF_OPT_ADAGRAD) vstore<VEC>(s1 + VEC * vi, a);
+    if (o.kind == RTF_OPT_ADAM) vstore<VEC>(s2 + VEC * vi, b);
+  }
+}
+
+struct SegWork {
+  const uint32_t* keys;       // sorted
+  const uint32_t* vals;       // sorted lookup positions
+  const uint32_t* seg_start;  // [n_seg + 1]
+  int32_t* counters;          // [0] n_seg [1] n_valid [2] slots used [3] long segments
+  uint2* long_list;           // (seg, slot_base)
+  uint2* slot_owner;          // (seg, chunk)
+  float* partials;            // [slot][dim_max]
+  uint32_t* uniq_key;
+  float* uniq_grad;
+  int dim_max;
+};
+
+// A: one lane-group per segment; short segments are finished here
+template <int VEC, int G, int VPL>
+__global__ void __launch_bounds__(256)
+seg_short(const __grid_constant__ BwdParams P, const __grid_constant__ SegWork S,
+          const float* __restrict__ grad) {
+  const long long gid = ((long long)blockIdx.x * blockDim.x + threadIdx.x) / G;
+  const int lg = (int)(threadIdx.x % G);
+  if (gid >= S.counters[1]) return;  // invalid-id segment (if any) is the last one
+  const uint32_t seg = (uint32_t)gid;
+  const uint32_t start = S.seg_start[seg], end = S.seg_start[seg + 1];
+  const uint32_t key = S.keys[start];
+  const uint32_t len = end - start;
+  if (len > RTF_SEG_CHUNK) {
+    const uint32_t nch = (len + RTF_SEG_CHUNK - 1) / RTF_SEG_CHUNK;
+    uint32_t slot0 = 0;
+    if (lg == 0) {
+      slot0 = (uint32_t)atomicAdd(&S.counters[2], (int)nch);
+      const int e = atomicAdd(&S.counters[3], 1);
+      S.long_list[e] = make_uint2(seg, slot0);
+    }
+    if (G > 1) {  // broadcast inside the lane-group only: other groups of the warp may not be here
+      const int g0 = (int)(threadIdx.x & 31) / G * G;
+      const uint32_t gmask = G == 32 ? 0xffffffffu : (((1u << (G & 31)) - 1u) << g0);
+      slot0 = __shfl_sync(gmask, slot0, g0);
+    }
+    for (uint32_t c = lg; c < nch; c += G) S.slot_owner[slot0 + c] = make_uint2(seg, c);
+    return;
+  }
+  const int nv = P.dim[key >> P.row_bits] / VEC;
+  Vec<VEC> acc[VPL];
+#pragma unroll
+  for (int k = 0; k < VPL; ++k)
+#pragma unroll
+    for (int e = 0; e < VEC; ++e) acc[k].v[e] = 0.f;
+  const float scale = __fdiv_rn(1.0f, (float)P.L);
+  sum_rows<VEC, G, VPL>(P, grad, S.vals, start, end, nv, lg, scale, acc);
+  finish_row<VEC, G, VPL>(P, key, seg, nv, lg, acc, S.uniq_key, S.uniq_grad, S.dim_max);
+}
+
+// B: one lane-group per chunk of a long segment -> partial sums
+template <int VEC, int G, int VPL>
+__global__ void __launch_bounds__(256)
+seg_partial(const __grid_constant__ BwdParams P, const __grid_constant__ SegWork S,
+            const float* __restrict__ grad) {
+  const long long gid = ((long long)blockIdx.x * blockDim.x + threadIdx.x) / G;
+  const int lg = (int)(threadIdx.x % G);
+  if (gid >= S.counters[2]) return;
+  const uint2 own = S.slot_owner[gid];
+  const uint32_t s0 = S.seg_start[own.x], s1 = S.seg_start[own.x + 1];
+  const uint32_t start = s0 + own.y * RTF_SEG_CHUNK;
+  const uint32_t end = min(start + RTF_SEG_CHUNK, s1);
+  const uint32_t key = S.keys[s0];
+  const int nv = P.dim[key >> P.row_bits] / VEC;
+  Vec<VEC> acc[VPL];
+#pragma unroll
+  for (int k = 0; k < VPL; ++k)
+#pragma unroll
+    for (int e = 0; e < VEC; ++e) acc[k].v[e] = 0.f;
+  const float scale = __fdiv_rn(1.0f, (float)P.L);
+  sum_rows<VEC, G, VPL>(P, grad, S.vals, start, end, nv, lg, scale, acc);
+#pragma unroll
+  for (int k = 0; k < VPL; ++k) {
+    const int vi = lg + k * G;
+    if (vi < nv) vstore<VEC>(S.partials + gid * S.dim_max + VEC * vi, acc[k]);
+  }
+}
+
+// C: one lane-group per long segment combines its chunk partials in chunk order
+template <int VEC, int G, int VPL>
+__global__ void __launch_bounds__(256)
+seg_combine(const __grid_constant__ BwdParams P, const __grid_constant__ SegWork S) {
+  const long long gid = ((long long)blockIdx.x * blockDim.x + threadIdx.x) / G;
+  const int lg = (int)(threadIdx.x % G);
+  if (gid >= S.counters[3]) return;
+  const uint2 ent = S.long_list[gid];
+  const uint32_t seg = ent.x;
+  const uint32_t start = S.seg_start[seg], end = S.seg_start[seg + 1];
+  const uint32_t nch = (end - start + RTF_SEG_CHUNK - 1) / RTF_SEG_CHUNK;
+  const uint32_t key = S.keys[start];
+  const int nv = P.dim[key >> P.row_bits] / VEC;
+  Vec<VEC> acc[VPL];
+#pragma unroll
+  for (int k = 0; k < VPL; ++k)
+#pragma unroll
+    for (int e = 0; e < VEC; ++e) acc[k].v[e] = 0.f;
+  constexpr int U = 4;
+  for (uint32_t c0 = 0; c0 < nch; c0 += U) {
+    Vec<VEC> x[U][VPL];
+#pragma unroll
+    for (int u = 0; u < U; ++u)
+#pragma unroll
+      for (int k = 0; k < VPL; ++k) {
+        const int vi = lg + k * G;
+        if (c0 + u < nch && vi < nv)
+          x[u][k] = vload<VEC>(S.partials + (long long)(ent.y + c0 + u) * S.dim_max + VEC * vi);
+      }
+#pragma unroll
+    for (int u = 0; u < U; ++u)
+      if (c0 + u < nch) {
+#pragma unroll
+        for (int k = 0; k < VPL; ++k) {
+          const int vi = lg + k * G;
+          if (vi < nv) {
+#pragma unroll
+            for (int e = 0; e < VEC; ++e) acc[k].v[e] = __fadd_rn(acc[k].v[e], x[u][k].v[e]);
+          }
+        }
+      }
+  }
+  finish_row<VEC, G, VPL>(P, key, seg, nv, lg, acc, S.uniq_key, S.uniq_grad, S.dim_max);
+}
+
+template <int VEC, int G, int VPL>
+static int launch_segments(const BwdParams& P, const SegWork& S, const float* grad, long long n,
+                           cudaStream_t st) {
+  const long long groups_a = n;                            // upper bound on segments
+  const long long groups_b = 2 * n / RTF_SEG_CHUNK + 2;    // upper bound on chunk slots
+  const long long groups_c = n / RTF_SEG_CHUNK + 1;        // upper bound on long segments
+  seg_short<VEC, G, VPL><<<(unsigned)((groups_a * G + 255) / 256), 256, 0, st>>>(P, S, grad);
+  seg_partial<VEC, G, VPL><<<(unsigned)((groups_b * G + 255) / 256), 256, 0, st>>>(P, S, grad);
+  seg_combine<VEC, G, VPL><<<(unsigned)((groups_c * G + 255) / 256), 256, 0, st>>>(P, S);
+  RTF_CHECK_LAUNCH();
+  return 0;
+}
+
+static inline size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
+
+struct WsLayout {
+  size_t keys0, keys1, vals0, vals1, hist, tile_sums, seg_start, counters, long_list, slot_owner,
+      partials, total;
+};
+static WsLayout ws_layout(long long n, int dim_max) {
+  WsLayout w;
+  const size_t nn = (size_t)(n > 0 ? n : 1);
+  const size_t nblk = (nn + SORT_TILE - 1) / SORT_TILE;
+  size_t o = 0;
+  auto take = [&](size_t bytes) { size_t r = o; o = align_up(o + bytes, 256); return r; };
+  w.keys0 = take(nn * 4);
+  w.keys1 = take(nn * 4);
+  w.vals0 = take(nn * 4);
+  w.vals1 = take(nn * 4);
+  w.hist = take(256 * nblk * 4);
+  const size_t scan_n = nn > 256 * nblk ? nn : 256 * nblk;
+  w.tile_sums = take(((scan_n + SCAN_TILE - 1) / SCAN_TILE + 1) * 4);
+  w.seg_start = take((nn + 1) * 4);
+  w.counters = take(16);
+  w.long_list = take((nn / RTF_SEG_CHUNK + 2) * 8);
+  w.slot_owner = take((2 * nn / RTF_SEG_CHUNK + 4) * 8);
+  w.partials = take((2 * nn / RTF_SEG_CHUNK + 4) * (size_t)dim_max * 4);
+  w.total = o;
+  return w;
+}
+
+}  // namespace rtf
+
+extern "C" int rtf_embed_bwd_workspace(int64_t n_lookups, int dim_max, size_t* bytes) {
+  if (!bytes || n_lookups < 0 || dim_max <= 0) return RTF_E_ARG;
+  *bytes = rtf::ws_layout(n_lookups, dim_max).total;
+  return 0;
+}
+
+extern "C" int rtf_embed_bwd(float* const* weights, float* const* state1, float* const* state2,
+                             const int64_t* rows, const int32_t* dims, int n_tables,
+                             const int32_t* field_table, int n_fields, const void* d_ids,
+                             int ids_i64, int64_t B, int L, int64_t ids_sb, int64_t ids_sf,
+                             int64_t ids_sl, int pool, const float* d_grad, int64_t grad_sb,
+                             const rtf_opt* opt, uint32_t* d_uniq_key, float* d_uniq_grad,
+                             int32_t* d_num_uniq, int* row_bits_out, void* d_workspace,
+                             size_t workspace_bytes, void* stream) {
+  using namespace rtf;
+  if (!weights || !rows || !dims || !field_table || !d_ids || !d_grad || !opt || !d_workspace)
+    return RTF_E_ARG;
+  if (n_tables <= 0 || n_fields <= 0 || B < 0 || L <= 0) return RTF_E_ARG;
+  if (n_tables > RTF_MAX_FIELDS || n_fields > RTF_MAX_FIELDS) return RTF_E_RANGE;
+  if (pool < RTF_POOL_NONE || pool > RTF_POOL_MEAN) return RTF_E_ARG;
+  if (opt->kind < RTF_OPT_NONE || opt->kind > RTF_OPT_ADAM) return RTF_E_ARG;
+  cudaStream_t st = (cudaStream_t)stream;
+
+  BwdParams P;
+  long long rows_max = 1;
+  int dim_max = 0;
+  bool vec_ok = ((uintptr_t)d_grad % 16 == 0) && (grad_sb % 4 == 0) &&
+                (!d_uniq_grad || (uintptr_t)d_uniq_grad % 16 == 0);
+  for (int t = 0; t < n_tables; ++t) {
+    if (rows[t] <= 0 || dims[t] <= 0) return RTF_E_ARG;
+    P.w[t] = weights[t];
+    P.s1[t] = state1 ? state1[t] : nullptr;
+    P.s2[t] = state2 ? state2[t] : nullptr;
+    P.rows[t] = rows[t];
+    P.dim[t] = dims[t];
+    if (opt->kind != RTF_OPT_NONE && !P.w[t]) return RTF_E_ARG;
+    if (opt->kind >= RTF_OPT_ADAGRAD && !P.s1[t]) return RTF_E_ARG;
+    if (opt->kind == RTF_OPT_ADAM && !P.s2[t]) return RTF_E_ARG;
+    if (dims[t] % 4 || (uintptr_t)P.w[t] % 16 || (uintptr_t)P.s1[t] % 16 ||
+        (uintptr_t)P.s2[t] % 16)
+      vec_ok = false;
+    if (rows[t] > rows_max) rows_max = rows[t];
+    if (dims[t] > dim_max) dim_max = dims[t];
+  }
+  int off = 0;
+  for (int f = 0; f < n_fields; ++f) {
+    const int t = field_table[f];
+    if (t < 0 || t >= n_tables) return RTF_E_ARG;
+    P.field_table[f] = t;
+    P.field_off[f] = off;
+    if (off % 4) vec_ok = false;
+    off += dims[t];
+  }
+  P.sumD = off;
+  if (off % 4) vec_ok = false;
+  int row_bits = 1;
+  while (((long long)1 << row_bits) < rows_max) ++row_bits;
+  int table_bits = 1;
+  while ((1 << table_bits) < n_tables + 1) ++table_bits;  // +1: sentinel table for bad ids
+  if (row_bits + table_bits > 32) return RTF_E_RANGE;
+  if (row_bits_out) *row_bits_out = row_bits;
+  P.n_tables = n_tables;
+  P.n_fields = n_fields;
+  P.row_bits = row_bits;
+  P.L = L;
+  P.pool = pool;
+  P.grad_sb = grad_sb;
+  P.opt = *opt;
+
+  const long long n = B * (long long)L * n_fields;
+  if (n >= 0x7fffffffLL) return RTF_E_RANGE;
+  if (n == 0) {
+    if (d_num_uniq) cudaMemsetAsync(d_num_uniq, 0, 4, st);
+    return 0;
+  }
+  if (dim_max > (vec_ok ? 512 : 128)) return RTF_E_RANGE;
+  const WsLayout W = ws_layout(n, dim_max);
+  if (workspace_bytes < W.total) return RTF_E_WORKSPACE;
+  if ((uintptr_t)d_workspace % 256) return RTF_E_ALIGN;
+  char* ws = (char*)d_workspace;
+  uint32_t* keys[2] = {(uint32_t*)(ws + W.keys0), (uint32_t*)(ws + W.keys1)};
+  uint32_t* vals[2] = {(uint32_t*)(ws + W.vals0), (uint32_t*)(ws + W.vals1)};
+  uint32_t* hist = (uint32_t*)(ws + W.hist);
+  uint32_t* tile_sums = (uint32_t*)(ws + W.tile_sums);
+  uint32_t* seg_start = (uint32_t*)(ws + W.seg_start);
+  int32_t* counters = (int32_t*)(ws + W.counters);
+
+  // 1. keys
+  const unsigned kb = (unsigned)((n + 255) / 256);
+  if (ids_i64)
+    make_keys<int64_t><<<kb, 256, 0, st>>>(P, (const int64_t*)d_ids, n, ids_sb, ids_sf, ids_sl,
+                                           keys[0]);
+  else
+    make_keys<int32_t><<<kb, 256, 0, st>>>(P, (const int32_t*)d_ids, n, ids_sb, ids_sf, ids_sl,
+                                           keys[0]);
+  RTF_CHECK_LAUNCH();
+
+  // 2. LSD radix sort over the significant bits
+  const int nblk = (int)((n + SORT_TILE - 1) / SORT_TILE);
+  const int total_bits = row_bits + table_bits;
+  int cur = 0;
+  for (int shift = 0, pass = 0; shift < total_bits; shift += 8, ++pass) {
+    sort_hist<<<nblk, SORT_THREADS, 0, st>>>(keys[cur], n, shift, hist, nblk);
+    int rc = exclusive_scan(InArray{hist}, OutArray{hist}, 256LL * nblk, tile_sums, st);
+    if (rc) return rc;
+    sort_scatter<<<nblk, SORT_THREADS, 0, st>>>(keys[cur], vals[cur], keys[cur ^ 1],
+                                                vals[cur ^ 1], n, shift, hist, nblk, pass == 0);
+    RTF_CHECK_LAUNCH();
+    cur ^= 1;
+  }
+
+  // 3. segments
+  cudaError_t ce = cudaMemsetAsync(counters, 0, 16, st);
+  if (ce != cudaSuccess) return (int)ce;
+  {
+    OutSegments outseg{keys[cur], seg_start, counters, d_num_uniq, n, (uint32_t)n_tables,
+                       row_bits};
+    int rc = exclusive_scan(InHeadFlag{keys[cur]}, outseg, n, tile_sums, st);
+    if (rc) return rc;
+  }
+
+  // 4. segment reduce + optimizer
+  SegWork S;
+  S.keys = keys[cur];
+  S.vals = vals[cur];
+  S.seg_start = seg_start;
+  S.counters = counters;
+  S.long_list = (uint2*)(ws + W.long_list);
+  S.slot_owner = (uint2*)(ws + W.slot_owner);
+  S.partials = (float*)(ws + W.partials);
+  S.uniq_key = d_uniq_key;
+  S.uniq_grad = d_uniq_grad;
+  S.dim_max = dim_max;
+
+  if (vec_ok) {
+    const int nv = dim_max / 4;
+    int G = 1;
+    while (G < nv && G < 32) G <<= 1;
+    const int vpl = (nv + G - 1) / G;
+    if (vpl == 1) {
+      switch (G) {
+        case 1: return launch_segments<4, 1, 1>(P, S, d_grad, n, st);
+        case 2: return launch_segments<4, 2, 1>(P, S, d_grad, n, st);
+        case 4: return launch_segments<4, 4, 1>(P, S, d_grad, n, st);
+        case 8: return launch_segments<4, 8, 1>(P, S, d_grad, n, st);
+        case 16: return launch_segments<4, 16, 1>(P, S, d_grad, n, st);
+        default: return launch_segments<4, 32, 1>(P, S, d_grad, n, st);
+      }
+    }
+    if (vpl == 2) return launch_segments<4, 32, 2>(P, S, d_grad, n, st);
+    return launch_segments<4, 32, 4>(P, S, d_grad, n, st);
+  }
+  {
+    int G = 1;
+    while (G < dim_max && G < 32) G <<= 1;
+    const int vpl = (dim_max + G - 1) / G;
+    if (vpl == 1) {
+      switch (G) {
+        case 1: return launch_segments<1, 1, 1>(P, S, d_grad, n, st);
+        case 2: return launch_segments<1, 2, 1>(P, S, d_grad, n, st);
+        case 4: return launch_segments<1, 4, 1>(P, S, d_grad, n, st);
+        case 8: return launch_segments<1, 8, 1>(P, S, d_grad, n, st);
+        case 16: return launch_segments<1, 16, 1>(P, S, d_grad, n, st);
+        default: return launch_segments<1, 32, 1>(P, S, d_grad, n, st);
+      }
+    }
+    if (vpl == 2) return launch_segments<1, 32, 2>(P, S, d_grad, n, st);
+    return launch_segments<1, 32, 4>(P, S, d_grad, n, st);
+  }
+}

@@ -1,0 +1,60 @@
+"""The C-ABI library loads and exports every symbol include/rtf_b200.h declares (no GPU)."""
+import ctypes
+import os
+import re
+
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+@pytest.fixture(scope="module")
+def built():
+    import __graft_entry__ as g
+    g.build()
+    import recommend_tf2_b200 as pkg
+    return pkg
+
+
+def _declared_symbols():
+    src = open(os.path.join(ROOT, "include", "rtf_b200.h")).read()
+    src = re.sub(r"/\*.*?\*/", "", src, flags=re.S)
+    return sorted(set(re.findall(r"\bint\s+(rtf_[a-z0-9_]+)\s*\(", src)))
+
+
+def test_header_symbols_are_exported(built):
+    names = _declared_symbols()
+    assert "rtf_embed_fwd" in names and "rtf_embed_bwd" in names
+    handle = ctypes.CDLL(built._lib.LIB_PATH)
+    for n in names:
+        assert hasattr(handle, n), f"{n} declared in rtf_b200.h but not exported"
+
+
+def test_python_binding_covers_header(built):
+    assert sorted(built._lib.SIGNATURES) == _declared_symbols()
+
+
+def test_version_and_arg_errors_without_gpu(built):
+    lib = built.lib()
+    arch = ctypes.c_int(0)
+    assert lib.rtf_version(ctypes.byref(arch)) >= 1 and arch.value == 100
+    # argument validation happens before any CUDA call
+    assert lib.rtf_embed_fwd(None, None, None, 0, None, 0, 0, 1, 0, 0, 0, 0, None, 0, None, None) == -1
+    nbytes = ctypes.c_size_t(0)
+    assert lib.rtf_embed_bwd_workspace(1 << 20, 128, ctypes.byref(nbytes)) == 0
+    assert nbytes.value > (1 << 20) * 16
+
+
+def test_product_path_has_no_cpu_fallback(built):
+    import torch
+    with pytest.raises(built.RtfError):
+        built.embed_fwd([torch.zeros(4, 4)], torch.zeros((2, 1), dtype=torch.int32))
+
+
+def test_product_package_never_imports_oracle():
+    pkg_dir = os.path.join(ROOT, "recommend-tf2.0_b200")
+    for dp, _, fns in os.walk(pkg_dir):
+        for fn in fns:
+            if fn.endswith((".py", ".cu", ".cuh", ".h")):
+                txt = open(os.path.join(dp, fn)).read()
+                assert "import oracle" not in txt and "from oracle" not in txt, fn

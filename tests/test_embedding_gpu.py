@@ -1,0 +1,235 @@
+"""K1/K2 parity (GPU, through the C-ABI) against the numpy oracle.
+
+Bar (north star): ids / gathered rows / index work bit-exact; fp32 sums bit-exact because the
+summation order is fixed on both sides; optimizer updates bit-exact (separately rounded ops).
+"""
+import numpy as np
+import pytest
+import torch
+
+from oracle import embedding as O
+
+pytestmark = pytest.mark.gpu
+
+
+def _zipf_ids(rng, B, F, L, rows, a=1.05):
+    ids = np.empty((B, F, L), np.int64)
+    for f in range(F):
+        ids[:, f, :] = (rng.zipf(a, size=(B, L)) - 1) % rows[f]
+    return ids
+
+
+def _tables(rng, rows, dims):
+    return [rng.uniform(-0.05, 0.05, size=(n, d)).astype(np.float32) for n, d in zip(rows, dims)]
+
+
+CASES = [
+    # name, B, rows, dims, L
+    ("dlrm_like", 257, [1460, 583, 100003, 3, 24, 12517], [128] * 6, 1),
+    ("fm_d8", 1024, [1000] * 26, [8] * 26, 1),
+    ("autoint_d16", 130, [50, 7, 999], [16] * 3, 1),
+    ("mixed_dims", 65, [10, 20, 30, 40], [4, 8, 64, 256], 1),
+    ("d512", 33, [100, 50], [512, 384], 1),
+    ("odd_dims_scalar", 37, [11, 13, 17], [3, 5, 10], 1),
+    ("one_sample", 1, [5], [128], 1),
+]
+
+
+@pytest.mark.parametrize("name,B,rows,dims,L", CASES, ids=[c[0] for c in CASES])
+@pytest.mark.parametrize("idt", [torch.int32, torch.int64])
+def test_gather_concat_bit_exact(rtf, name, B, rows, dims, L, idt):
+    rng = np.random.default_rng(0)
+    tabs = _tables(rng, rows, dims)
+    ids = _zipf_ids(rng, B, len(rows), L, rows)
+    want = O.embed_lookup_concat(tabs, ids)[:, 0, :]
+    dtabs = [torch.from_numpy(t).cuda() for t in tabs]
+    dids = torch.from_numpy(ids[:, :, 0]).to(idt).cuda()
+    err = torch.zeros(1, dtype=torch.int32, device="cuda")
+    got = rtf.embed_fwd(dtabs, dids, "BF", None, err=err)
+    assert got.shape == want.shape
+    assert np.array_equal(got.cpu().numpy().view(np.uint32), want.view(np.uint32))
+    assert int(err.item()) == 0
+
+
+@pytest.mark.parametrize("pool", [None, "sum", "mean"])
+@pytest.mark.parametrize("layout", ["BFL", "BLF"])
+@pytest.mark.parametrize("dims", [[8, 8, 8], [64, 64], [128], [6, 10]])
+def test_sequence_lookup_and_pooling(rtf, pool, layout, dims):
+    rng = np.random.default_rng(1)
+    F, B, L = len(dims), 41, 13
+    rows = [37 + 11 * f for f in range(F)]
+    tabs = _tables(rng, rows, dims)
+    ids = _zipf_ids(rng, B, F, L, rows)
+    want = O.embed_lookup_concat(tabs, ids, pool)
+    dtabs = [torch.from_numpy(t).cuda() for t in tabs]
+    t_ids = torch.from_numpy(ids).to(torch.int32).cuda()
+    if layout == "BLF":
+        t_ids = t_ids.permute(0, 2, 1).contiguous()
+    got = rtf.embed_fwd(dtabs, t_ids, layout, pool)
+    assert got.shape == want.shape
+    assert np.array_equal(got.cpu().numpy().view(np.uint32), want.view(np.uint32))
+
+
+def test_shared_table_and_strided_ids(rtf):
+    """DIN shares the item tables between the target item and the behaviour sequence
+    (src/ctr/din/model.py:71-72) and indexes columns of one wide id matrix."""
+    rng = np.random.default_rng(2)
+    item = rng.normal(0, 0.05, (1000, 8)).astype(np.float32)
+    cate = rng.normal(0, 0.05, (50, 8)).astype(np.float32)
+    B, L = 64, 10
+    wide = np.stack([rng.integers(0, 1000, (B, L)), rng.integers(0, 50, (B, L))], -1)  # (B,L,2)
+    want = O.embed_lookup_concat([item, cate], np.transpose(wide, (0, 2, 1)))
+    flat = torch.from_numpy(wide.reshape(B, 2 * L)).to(torch.int32).cuda()   # (B, 2*maxlen)
+    view = flat.view(B, L, 2)
+    got = rtf.embed_fwd([torch.from_numpy(item).cuda(), torch.from_numpy(cate).cuda()], view, "BLF")
+    assert np.array_equal(got.cpu().numpy(), want)
+
+
+def test_out_of_range_id_sets_flag_and_reads_zero(rtf):
+    tab = torch.arange(40, dtype=torch.float32, device="cuda").view(10, 4) + 1
+    ids = torch.tensor([[3], [10], [-1], [9]], dtype=torch.int32, device="cuda")
+    err = torch.zeros(1, dtype=torch.int32, device="cuda")
+    got = rtf.embed_fwd([tab], ids, "BF", None, err=err).cpu().numpy()
+    assert int(err.item()) == 1
+    assert np.array_equal(got[0], tab[3].cpu().numpy()) and np.array_equal(got[3], tab[9].cpu().numpy())
+    assert not got[1].any() and not got[2].any()
+    with pytest.raises(IndexError):
+        O.embed_lookup_concat([tab.cpu().numpy()], ids.cpu().numpy()[:, :, None])
+    ts = rtf.EmbeddingTables([10], [4])
+    ts.lookup(ids)
+    with pytest.raises(IndexError):
+        ts.check_ids()
+
+
+def test_empty_batch(rtf):
+    tab = torch.zeros(10, 8, device="cuda")
+    ids = torch.zeros((0, 1), dtype=torch.int32, device="cuda")
+    assert rtf.embed_fwd([tab], ids).shape == (0, 8)
+
+
+def test_cpu_tensor_raises(rtf):
+    with pytest.raises(rtf.RtfError):
+        rtf.embed_fwd([torch.zeros(4, 4)], torch.zeros((2, 1), dtype=torch.int32))
+
+
+# ------------------------------------------------------------------ backward
+BWD_CASES = [
+    # name, B, rows, dims, field_table, L, pool
+    ("dlrm_like", 300, [1460, 3, 100003, 24], [128] * 4, [0, 1, 2, 3], 1, None),
+    ("hot_rows_long_segments", 1500, [3, 2, 50], [128, 128, 128], [0, 1, 2], 1, None),
+    ("fm_d8", 1024, [1000] * 26, [8] * 26, list(range(26)), 1, None),
+    ("shared_table_seq", 50, [200, 20], [16, 16], [0, 1, 0, 1], 7, None),
+    ("pool_sum", 40, [30, 300], [64, 64], [0, 1], 9, "sum"),
+    ("pool_mean", 40, [30, 300], [32, 32], [0, 1], 9, "mean"),
+    ("mixed_dims", 70, [10, 20, 30], [4, 64, 256], [0, 1, 2], 1, None),
+    ("odd_dims_scalar", 90, [11, 13], [3, 10], [0, 1], 2, None),
+]
+
+
+def _bwd_inputs(case, seed=3):
+    name, B, rows, dims, ft, L, pool = case
+    rng = np.random.default_rng(seed)
+    F = len(ft)
+    frows = [rows[t] for t in ft]
+    ids = _zipf_ids(rng, B, F, L, frows)
+    sumD = sum(dims[t] for t in ft)
+    gshape = (B, L, sumD) if pool is None else (B, sumD)
+    grad = rng.normal(0, 1, gshape).astype(np.float32)
+    return rng, ids, grad
+
+
+@pytest.mark.parametrize("case", BWD_CASES, ids=[c[0] for c in BWD_CASES])
+def test_grad_segments_bit_exact(rtf, case):
+    name, B, rows, dims, ft, L, pool = case
+    rng, ids, grad = _bwd_inputs(case)
+    keys_w, tot_w, rb_w = O.embed_grad_unique(ids, ft, rows, dims, grad, pool)
+    weights = [torch.zeros(n, d, device="cuda") for n, d in zip(rows, dims)]
+    dids = torch.from_numpy(ids).to(torch.int32).cuda()
+    keys, tot, rb = rtf.embed_bwd(weights, ft, dids, torch.from_numpy(grad).cuda(), "BFL", pool,
+                                  want_unique=True)
+    assert rb == rb_w
+    assert np.array_equal(keys.cpu().numpy(), keys_w)                      # sorted unique keys
+    assert np.array_equal(tot.cpu().numpy().view(np.uint32), tot_w.view(np.uint32))
+    # and against an order-free fp64 dense scatter-add
+    dense = O.dense_reference_grad([(n, d) for n, d in zip(rows, dims)], ids, ft, grad, pool)
+    tab, row = keys_w >> rb_w, keys_w & ((1 << rb_w) - 1)
+    for t in range(len(rows)):
+        sel = tab == t
+        np.testing.assert_allclose(tot_w[sel, : dims[t]], dense[t][row[sel]], rtol=1e-4, atol=1e-4)
+
+
+@pytest.mark.parametrize("kind", ["sgd", "adagrad", "adam"])
+@pytest.mark.parametrize("case", [BWD_CASES[0], BWD_CASES[1], BWD_CASES[3], BWD_CASES[5], BWD_CASES[7]],
+                         ids=lambda c: c[0])
+def test_sparse_optimizer_in_place_bit_exact(rtf, kind, case):
+    name, B, rows, dims, ft, L, pool = case
+    rng, ids, grad = _bwd_inputs(case, seed=4)
+    W = _tables(rng, rows, dims)
+    S1 = [np.abs(rng.normal(0, 0.01, w.shape)).astype(np.float32) for w in W]
+    S2 = [np.abs(rng.normal(0, 0.01, w.shape)).astype(np.float32) for w in W]
+    dW = [torch.from_numpy(w.copy()).cuda() for w in W]
+    dS1 = [torch.from_numpy(w.copy()).cuda() for w in S1]
+    dS2 = [torch.from_numpy(w.copy()).cuda() for w in S2]
+    opt = rtf.SparseOptimizer(kind, lr=0.01, l2=1e-4)
+    st = opt.struct_for_step(3)
+    O.embed_bwd_apply(kind, W, S1, S2, ids, ft, grad, pool, lr=np.float32(st.lr), l2=1e-4)
+    rtf.embed_bwd(dW, ft, torch.from_numpy(ids).to(torch.int64).cuda(), torch.from_numpy(grad).cuda(),
+                  "BFL", pool, opt=st, state1=dS1, state2=dS2)
+    for t in range(len(W)):
+        assert np.array_equal(dW[t].cpu().numpy().view(np.uint32), W[t].view(np.uint32)), f"W[{t}]"
+        if kind in ("adagrad", "adam"):
+            assert np.array_equal(dS1[t].cpu().numpy().view(np.uint32), S1[t].view(np.uint32))
+        if kind == "adam":
+            assert np.array_equal(dS2[t].cpu().numpy().view(np.uint32), S2[t].view(np.uint32))
+
+
+def test_backward_is_run_to_run_deterministic(rtf):
+    case = ("det", 4096, [5, 1000, 100000], [128] * 3, [0, 1, 2], 1, None)
+    rng, ids, grad = _bwd_inputs(case)
+    dids = torch.from_numpy(ids).to(torch.int32).cuda()
+    g = torch.from_numpy(grad).cuda()
+    outs = []
+    for _ in range(3):
+        W = [torch.zeros(n, 128, device="cuda") for n in case[2]]
+        k, t, _ = rtf.embed_bwd(W, case[4], dids, g, "BFL", None, want_unique=True)
+        outs.append((k.clone(), t.clone()))
+    for k, t in outs[1:]:
+        assert torch.equal(k, outs[0][0]) and torch.equal(t, outs[0][1])
+
+
+def test_large_sort_matches_torch_sort(rtf):
+    """Full-size index work: 2^20+ lookups, sorted unique keys must equal torch.unique."""
+    g = torch.Generator(device="cpu").manual_seed(5)
+    B, F = 70001, 16
+    rows = [10_000_000] * 4 + [100_000] * 4 + [1000] * 4 + [7] * 4
+    ids = torch.stack([torch.randint(0, r, (B,), generator=g) for r in rows], 1).to(torch.int32).cuda()
+    weights = [torch.empty((r, 4), device="cuda") for r in rows]   # 4 floats/row: 640 MB total max
+    grad = torch.ones(B, F * 4, device="cuda")
+    keys, tot, rb = rtf.embed_bwd(weights, list(range(F)), ids, grad, "BF", None, want_unique=True)
+    want = torch.unique((torch.arange(F, device="cuda").view(1, F).long() << rb) | ids.long())
+    assert torch.equal(keys, want)
+    # counts: every summed gradient equals the multiplicity of the key (grad rows are all ones)
+    _, counts = torch.unique((torch.arange(F, device="cuda").view(1, F).long() << rb) | ids.long(),
+                             return_counts=True)
+    assert torch.equal(tot[:, 0], counts.float())
+
+
+def test_autograd_lookup_fused_and_sparse(rtf):
+    rng = np.random.default_rng(6)
+    rows, dims = [50, 60], [16, 16]
+    ids = torch.from_numpy(_zipf_ids(rng, 32, 2, 1, rows)[:, :, 0]).to(torch.int32).cuda()
+    ts = rtf.EmbeddingTables(rows, dims, seed=0)
+    out = ts.lookup(ids)
+    (out * out).sum().backward()
+    ref = [w.detach().clone().requires_grad_(True) for w in ts.weights]
+    o2 = torch.cat([ref[0][ids[:, 0].long()], ref[1][ids[:, 1].long()]], 1)
+    (o2 * o2).sum().backward()
+    for w, r in zip(ts.weights, ref):
+        torch.testing.assert_close(w.grad.to_dense(), r.grad, rtol=1e-5, atol=1e-6)
+    # fused SGD: W <- W - lr * g
+    ts2 = rtf.EmbeddingTables(rows, dims, seed=0, optimizer=rtf.SparseOptimizer("sgd", lr=0.5))
+    ts2.begin_step()
+    out = ts2.lookup(ids)
+    (out * out).sum().backward()
+    for w2, r in zip(ts2.weights, ref):
+        torch.testing.assert_close(w2.detach(), r.detach() - 0.5 * r.grad, rtol=1e-5, atol=1e-6)
