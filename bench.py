@@ -1,0 +1,360 @@
+#!/usr/bin/env python
+"""bench.py — DLRM training throughput on synthetic Criteo-shaped data (BASELINE.json configs[1]).
+
+    python bench.py --gpus N --steps K --warmup W          # this repo's CUDA path
+    python bench.py --impl reference --gpus N ...          # the reference op sequence on host cores
+
+A step = one full training pass of the hot path over one batch: bottom MLP, fused embedding
+gather + pairwise-dot interaction (K1+K4), top MLP, Keras BCE, backward (K4 bwd), deterministic
+embedding backward with in-place sparse Adam (K2), dense Adam.  Prints ONE JSON line.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+# Criteo-Kaggle cardinalities capped at 10 M rows
+CRITEO_ROWS = [min(n, 10_000_000) for n in (
+    1460, 583, 10131227, 2202608, 305, 24, 12517, 633, 3, 93145, 5683, 8351593, 3194, 27, 14992,
+    5461306, 10, 5652, 2173, 4, 7046547, 18, 15, 286181, 105, 142572)]
+EMBED_DIM = 128
+N_DENSE = 13
+BOT_MLP = (512, 256, 128)
+TOP_MLP = (1024, 1024, 512, 256)
+
+
+def parse_args():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--batch", type=int, default=65536, help="samples per GPU per step")
+    ap.add_argument("--ids", default="uniform", choices=["uniform", "zipf"])
+    ap.add_argument("--cpu-batch", type=int, default=2048)
+    ap.add_argument("--cpu-row-cap", type=int, default=1_000_000)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-kernel-timing", action="store_true")
+    return ap.parse_args()
+
+
+def load_peaks():
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(path):
+        with open(path) as f:
+            return json.load(f), "measured (MEASURED_PEAKS.json)"
+    return {"hbm_gbs": 6650.0, "bf16_tflops": 1590.0}, "fallback (B200_PROFILING.md)"
+
+
+def make_batches(n, B, rows, ids_kind, seed):
+    """Synthetic Criteo-shaped batches in pinned host memory: dense U[0,1) (B,13) f32, sparse
+    (B,26) i32 (uniform or Zipf(1.05) mod N_t), labels Bernoulli(0.25)."""
+    import numpy as np
+    import torch
+    rng = np.random.default_rng(seed)
+    out = []
+    for _ in range(n):
+        dense = rng.random((B, N_DENSE), dtype=np.float32)
+        if ids_kind == "uniform":
+            sparse = np.stack([rng.integers(0, r, B, dtype=np.int64) for r in rows], 1)
+        else:
+            sparse = np.stack([(rng.zipf(1.05, B) - 1) % r for r in rows], 1)
+        y = (rng.random((B, 1)) < 0.25).astype(np.float32)
+        out.append((torch.from_numpy(dense), torch.from_numpy(sparse.astype(np.int32)),
+                    torch.from_numpy(y)))
+    return out
+
+
+class ClockSampler:
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index):
+        self.proc = None
+        try:
+            self.proc = subprocess.Popen(
+                ["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "100",
+                 "-i", str(gpu_index)], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+        except OSError:
+            pass
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        try:
+            out, _ = self.proc.communicate(timeout=5)
+        except subprocess.TimeoutExpired:
+            self.proc.kill()
+            out, _ = self.proc.communicate()
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for line in out.splitlines():
+            parts = [p.strip() for p in line.split(",")]
+            if len(parts) < 7:
+                continue
+            try:
+                sm.append(float(parts[0]))
+                mx.append(float(parts[1]))
+            except ValueError:
+                continue
+            for nm, v in zip(names, parts[3:7]):
+                if v.lower().startswith("active"):
+                    reasons.add(nm)
+        return {"sm_mhz": statistics.median(sm) if sm else None,
+                "sm_max_mhz": max(mx) if mx else None, "reasons": sorted(reasons),
+                "samples": len(sm)}
+
+
+def cpu_reference_run(args, steps, warmup):
+    """The reference op sequence on host cores (oracle/dlrm_ref.py), bounded sample."""
+    import torch
+    from oracle import dlrm_ref
+    rows = [min(r, args.cpu_row_cap) for r in CRITEO_ROWS]
+    batches = make_batches(warmup + steps, args.cpu_batch, rows, args.ids, seed=1)
+    batches = [(d, s, y) for d, s, y in batches]
+    sps, threads, sec_step = dlrm_ref.time_cpu_train(rows, EMBED_DIM, BOT_MLP, TOP_MLP, batches,
+                                                     warmup=warmup, threads=os.cpu_count())
+    sample = (f"{steps} steps x {args.cpu_batch} samples, tables capped at {args.cpu_row_cap} rows "
+              f"(host RAM), sparse-row Adam; torch-CPU restatement of the reference op sequence, "
+              f"not TensorFlow")
+    return {"value": sps, "unit": "samples/s", "cores": threads, "kind": "port", "sample": sample,
+            "ms_per_step": sec_step * 1e3}
+
+
+def bench_config(args, world):
+    return {"workload": "dlrm_criteo_synthetic", "tables": len(CRITEO_ROWS),
+            "rows_total": sum(CRITEO_ROWS), "embed_dim": EMBED_DIM, "bot_mlp": list(BOT_MLP),
+            "top_mlp": list(TOP_MLP), "interaction": "dot", "batch_per_gpu": args.batch,
+            "global_batch": args.batch * world, "ids": args.ids,
+            "optimizer": "adam (sparse rows fused in K2, dense MLP torch fused)",
+            "l2_flush": "inputs larger than L2: 17.2 GB of tables, distinct batch every step",
+            "parallelism": "single" if world == 1 else f"tables sharded over {world} GPUs + dp MLP"}
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    world = int(os.environ.get("WORLD_SIZE", str(args.gpus)))
+    r = cpu_reference_run(args, args.steps, max(args.warmup, 1))
+    line = {"metric": "dlrm_train_samples_per_sec", "value": r["value"], "unit": "samples/s",
+            "impl": "reference", "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": r["ms_per_step"], "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": bench_config(args, world),
+            "cpu_baseline": {k: r[k] for k in ("value", "unit", "cores", "kind", "sample")},
+            "e2e": {"value": r["value"], "unit": "samples/s", "h2d_bytes_per_step": 0,
+                    "d2h_bytes_per_step": 0}}
+    print(json.dumps(line), flush=True)
+
+
+def embed_bwd_launches(rows, n_tables):
+    row_bits = max(1, (max(rows) - 1).bit_length())
+    table_bits = max(1, n_tables.bit_length())
+    passes = (row_bits + table_bits + 7) // 8
+    return 1 + passes * 5 + 3 + 3   # keys + passes*(hist + 3 scan + scatter) + seg scan + A/B/C
+
+
+def time_kernels(pkg, model, dev_batches, peaks_gbs):
+    """Per-kernel CUDA-event timing of the hot-path launches on the bench's own batches."""
+    import torch
+    from recommend_tf2_b200 import _lib as L
+    ts = model.embed_layers
+    F, D = len(ts.weights), EMBED_DIM
+    cols = pkg.dot_out_cols(F + 1, D, model.pad_to)
+    res = {}
+
+    def timed(fn, n):
+        torch.cuda.synchronize()
+        evs = []
+        for i in range(n):
+            a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            a.record()
+            fn(i)
+            b.record()
+            evs.append((a, b))
+        torch.cuda.synchronize()
+        return statistics.mean(a.elapsed_time(b) for a, b in evs)
+
+    n = len(dev_batches)
+    B = dev_batches[0][1].shape[0]
+    dense_rows = [torch.randn(B, D, device="cuda") for _ in range(2)]
+    gout = torch.randn(B, cols, device="cuda")
+    gemb = torch.randn(B, F * D, device="cuda")
+    tables = list(ts.weights)
+
+    # K1 standalone (the "embedding-lookup HBM GB/s" half of the metric)
+    out = torch.empty(B, F * D, device="cuda")
+    ms = timed(lambda i: pkg.embed_fwd(tables, dev_batches[i][1], "BF", None, out=out), n)
+    by = B * F * (4 + D * 4 + D * 4)
+    res["embed_fwd_vec(K1)"] = (ms, by)
+    # fused K1+K4 forward / backward
+    with torch.no_grad():
+        ms = timed(lambda i: pkg.embed_dot(ts, dev_batches[i][1], dense_rows[i % 2], pad_to=model.pad_to), n)
+    by = B * (F * (4 + D * 4) + D * 4 + cols * 4)
+    res["dot_fwd_kernel(K1+K4)"] = (ms, by)
+    import ctypes as C
+    from recommend_tf2_b200.embedding import _ptr_array
+    rows_arr = L.host_array(C.c_int64, [int(t.shape[0]) for t in tables])
+    gdense = torch.empty(B, D, device="cuda")
+
+    def bwd(i):
+        ids = dev_batches[i][1]
+        L.check(L.lib().rtf_embed_dot_bwd(_ptr_array(tables), rows_arr, F, D, ids.data_ptr(), 0, B,
+                                          ids.stride(0), ids.stride(1), dense_rows[i % 2].data_ptr(), D,
+                                          gout.data_ptr(), cols, gdense.data_ptr(), D, gemb.data_ptr(),
+                                          F * D, L.current_stream_ptr()), "rtf_embed_dot_bwd")
+    ms = timed(bwd, n)
+    by = B * (F * (4 + D * 4) + D * 4 + cols * 4 + D * 4 + F * D * 4)
+    res["dot_bwd_kernel(K4 bwd)"] = (ms, by)
+    # K2 pipeline with Adam (whole call: keys + radix sort + segments + reduce/update)
+    opt = ts.optimizer.struct_for_step(max(ts.optimizer.step, 1))
+    uniq = []
+    for i in range(n):
+        ids = dev_batches[i][1].long()
+        keys = ids + (torch.arange(F, device="cuda").view(1, F) << 32)
+        uniq.append(int(torch.unique(keys).numel()))
+
+    def k2(i):
+        pkg.embed_bwd([w.data for w in ts.weights], list(range(F)), dev_batches[i][1], gemb, "BF", None,
+                      opt=opt, state1=ts.state1, state2=ts.state2)
+    ms = timed(k2, n)
+    by = B * F * (4 + D * 4) + statistics.mean(uniq) * 6 * D * 4
+    res["embed_bwd(K2 sort+segment+adam)"] = (ms, by)
+    out = {}
+    for k, (ms, by) in res.items():
+        gbs = by / (ms * 1e-3) / 1e9
+        out[k] = {"ms": round(ms, 4), "algorithmic_bytes": int(by), "gbs": round(gbs, 1),
+                  "frac_hbm": round(gbs / peaks_gbs, 4)}
+    return out
+
+
+def run_b200(args):
+    import torch
+    import torch.distributed as dist
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device — the B200 path has no CPU fallback "
+                         "(use --impl reference for the host baseline)")
+    torch.cuda.set_device(local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    torch.backends.cuda.matmul.allow_tf32 = False   # fp32 parity with the reference (1e-5)
+    torch.backends.cudnn.allow_tf32 = False
+
+    import recommend_tf2_b200 as pkg
+    pkg.lib()
+    peaks, peak_src = load_peaks()
+
+    B = args.batch
+    K, W = args.steps, max(args.warmup, 3)
+    fc = [[{"feat": f"I{i}"} for i in range(N_DENSE)],
+          [{"feat": f"C{i}", "feat_num": r, "embed_dim": EMBED_DIM} for i, r in enumerate(CRITEO_ROWS)]]
+    if world == 1:
+        model = pkg.DLRM(fc, BOT_MLP, TOP_MLP, interaction="dot", seed=1234)
+        trainer = pkg.DLRMTrainer(model, lr=1e-3)
+    else:
+        from recommend_tf2_b200.sharded import ShardedDLRM, ShardedDLRMTrainer
+        model = ShardedDLRM(fc, BOT_MLP, TOP_MLP, seed=1234)
+        trainer = ShardedDLRMTrainer(model, lr=1e-3)
+
+    host = make_batches(W + K, B, CRITEO_ROWS, args.ids, seed=1000 + rank)
+    host = [tuple(t.pin_memory() for t in b) for b in host]
+    dev = [tuple(t.cuda(non_blocking=True) for t in b) for b in host]
+    torch.cuda.synchronize()
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    # ---- device-resident timing (value)
+    for i in range(W):
+        trainer.step(*dev[i])
+    barrier()
+    sampler = ClockSampler(local_rank) if rank == 0 else None
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for i in range(W, W + K):
+        trainer.step(*dev[i])
+    e1.record()
+    barrier()
+    ms_total = e0.elapsed_time(e1)
+    clocks = sampler.stop() if sampler else None
+
+    # ---- end to end: pinned host batches in, loss out, every step, inside the timed region
+    loss_host = torch.zeros(K, dtype=torch.float32).pin_memory()
+    barrier()
+    f0, f1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    f0.record()
+    for i in range(W, W + K):
+        d, s, y = (t.cuda(non_blocking=True) for t in host[i])
+        loss = trainer.step(d, s, y)
+        loss_host[i - W].copy_(loss, non_blocking=True)
+    f1.record()
+    barrier()
+    ms_e2e = f0.elapsed_time(f1)
+    model.embed_layers.check_ids()
+
+    t = torch.tensor([ms_total, ms_e2e], dtype=torch.float64, device="cuda")
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms_total, ms_e2e = float(t[0]), float(t[1])
+    h2d = sum(x.numel() * x.element_size() for x in host[0])
+
+    if rank == 0:
+        kernels = None
+        roof = None
+        if not args.no_kernel_timing and world == 1:
+            kernels = time_kernels(pkg, model, dev[W:W + min(K, 8)], peaks["hbm_gbs"])
+            top = max(kernels.items(), key=lambda kv: kv[1]["ms"])
+            roof = {"kernel": top[0], "bound": "hbm", "achieved": top[1]["gbs"],
+                    "peak": peaks["hbm_gbs"], "unit": "GB/s", "frac": top[1]["frac_hbm"],
+                    "traffic": None, "peak_source": peak_src,
+                    "algorithmic_bytes_per_launch": top[1]["algorithmic_bytes"],
+                    "ms_per_launch": top[1]["ms"]}
+        cpu = None
+        if not args.no_cpu_baseline:
+            cpu = cpu_reference_run(args, steps=3, warmup=1)
+            cpu = {k: cpu[k] for k in ("value", "unit", "cores", "kind", "sample")}
+        per_step = 2 + embed_bwd_launches(CRITEO_ROWS, len(CRITEO_ROWS))
+        line = {"metric": "dlrm_train_samples_per_sec", "value": B * world * K / (ms_total * 1e-3),
+                "unit": "samples/s", "n_gpus": world, "steps": K, "warmup": W,
+                "ms_per_step": ms_total / K, "higher_is_better": True, "scaling": "weak",
+                "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+                "config": bench_config(args, world), "clocks": clocks,
+                "e2e": {"value": B * world * K / (ms_e2e * 1e-3), "unit": "samples/s",
+                        "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 4,
+                        "ms_per_step": ms_e2e / K},
+                "gpu_launches": per_step * K, "roofline": roof, "kernels": kernels,
+                "cpu_baseline": cpu, "final_loss": float(loss_host[-1])}
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    args = parse_args()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_b200(args)
+
+
+if __name__ == "__main__":
+    main()

@@ -97,6 +97,34 @@ int rtf_embed_bwd(float* const* weights, float* const* state1, float* const* sta
                   uint32_t* d_uniq_key, float* d_uniq_grad, int32_t* d_num_uniq,
                   int* row_bits_out, void* d_workspace, size_t workspace_bytes, void* stream);
 
+/* ---- K4: DLRM pairwise dot interaction ------------------------------------------
+ * replaces: the missing interaction at src/ctr/dlrm/model.py:48 (the file concatenates;
+ *           the op is defined from the paper it cites at :7)
+ * X (B,F1,D) -> out[b] = [ X[b,0,:] | <X[b,i],X[b,j]> for i in 1..F1-1, j in 0..i-1 ]
+ * out_cols >= D + F1(F1-1)/2 columns are written (extra columns are zero padding, so the
+ * caller may round the top-MLP input width up); out_sb >= out_cols.  D % 4 == 0, F1 <= 64.
+ * _bwd: d_gx[b,i,:] = sum_j S[i][j] X[b,j,:] (+ gout[b,:D] on row 0), S = sym(dZ).     */
+int rtf_dot_interact_fwd(const float* d_x, int64_t B, int F1, int D, float* d_out,
+                         int64_t out_sb, int out_cols, void* stream);
+int rtf_dot_interact_bwd(const float* d_x, const float* d_gout, int64_t gout_sb, int64_t B,
+                         int F1, int D, float* d_gx, void* stream);
+
+/* ---- K1+K4 fused: gather the F embedding rows of a sample straight into shared memory
+ * (one TMA bulk copy per row), append the bottom-MLP row, interact, write (B, out_cols).
+ * replaces: src/ctr/dlrm/model.py:45-48 (lookup + concat + interaction) in one launch.
+ * X[b,0] = d_dense[b], X[b,1+f] = tables[f][ids[b*sb + f*sf]].  All tables have dim D.
+ * _bwd re-gathers X (tables must not have been updated since _fwd) and writes
+ * d_gdense (B,D) and d_gemb (B, F*D) — the latter is K2's d_grad.                        */
+int rtf_embed_dot_fwd(const float* const* tables, const int64_t* rows, int n_fields, int D,
+                      const void* d_ids, int ids_i64, int64_t B, int64_t ids_sb, int64_t ids_sf,
+                      const float* d_dense, int64_t dense_sb, float* d_out, int64_t out_sb,
+                      int out_cols, int32_t* d_err, void* stream);
+int rtf_embed_dot_bwd(const float* const* tables, const int64_t* rows, int n_fields, int D,
+                      const void* d_ids, int ids_i64, int64_t B, int64_t ids_sb, int64_t ids_sf,
+                      const float* d_dense, int64_t dense_sb, const float* d_gout,
+                      int64_t gout_sb, float* d_gdense, int64_t gdense_sb, float* d_gemb,
+                      int64_t gemb_sb, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

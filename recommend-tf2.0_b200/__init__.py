@@ -6,6 +6,10 @@ library or a CUDA device is missing."""
 from . import _lib
 from ._lib import RtfError, build, lib
 from .embedding import EmbeddingTables, SparseOptimizer, embed_bwd, embed_fwd
+from .interaction import dot_interact, dot_out_cols, embed_dot
+from . import layers
+from .dlrm import DLRM, DLRMTrainer
 
 __all__ = ["RtfError", "build", "lib", "EmbeddingTables", "SparseOptimizer", "embed_fwd",
-           "embed_bwd"]
+           "embed_bwd", "dot_interact", "dot_out_cols", "embed_dot", "layers", "DLRM",
+           "DLRMTrainer"]

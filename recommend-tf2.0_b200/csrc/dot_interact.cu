@@ -1,0 +1,386 @@
+// K4 — DLRM pairwise dot interaction, optionally fused with the embedding gather.
+//
+// The reference's DLRM.call concatenates instead of interacting (src/ctr/dlrm/model.py:48) and
+// cites arXiv 1906.00091 (:7); SURVEY.md §8 a5 defines the op from the paper:
+//   X = stack([bottom_mlp(dense), e_1 .. e_F])  (B, F1, D),  Z = X X^T,
+//   out = concat([X[:,0,:], Z[i,j] for i > j (row-major lower triangle)])   (B, D + F1(F1-1)/2)
+//
+// One warp owns one sample at a time.  Its F1 rows are staged in shared memory by the TMA
+// engine — one cp.async.bulk (SASS UBLKCP) per row, straight from the embedding tables when
+// fused, so gathered rows never round-trip HBM — completing on a per-warp mbarrier.  The
+// Gram matrix is computed in fp32 FFMA with 4x4 register blocks (lane <-> block of the lower
+// triangle); rows of a block are interleaved with stride F1p/4 so the 128-bit shared loads of
+// a warp hit distinct banks.  Backward re-gathers X (cheaper than saving it) and forms
+// dX = (S + S^T) X with lanes owning 4 embedding columns each.
+// Bound: HBM (ids + rows in, D+P floats out) with the fp32 FMA pipe close behind.
+#include "rtf_common.cuh"
+
+namespace rtf {
+
+struct DotParams {
+  const float* table[RTF_MAX_FIELDS];  // gather mode: row i >= 1 comes from table[i-1]
+  long long rows[RTF_MAX_FIELDS];
+  const void* ids;
+  long long ids_sb, ids_sf;
+  const float* dense;  // gather mode: row 0 (B, D)
+  long long dense_sb;
+  const float* x;  // stacked mode: (B, F1, D); null in gather mode
+  long long B;
+  int F1, D, out_cols;
+  float* out;  // fwd (B, out_cols...)
+  long long out_sb;
+  const float* gout;  // bwd
+  long long gout_sb;
+  float* gx;      // stacked mode (B, F1, D)
+  float* gdense;  // gather mode (B, D)
+  long long gdense_sb;
+  float* gemb;  // gather mode (B, F*D)
+  long long gemb_sb;
+  int32_t* err;
+};
+
+__host__ __device__ inline int dot_row_stride(int D) { return D + ((D % 8 == 0) ? 4 : 8); }
+
+template <typename IdT>
+__device__ __forceinline__ const float* dot_src_row(const DotParams& P, long long b, int i) {
+  if (P.x) return P.x + (b * P.F1 + i) * (long long)P.D;
+  if (i == 0) return P.dense + b * P.dense_sb;
+  const long long id = load_id((const IdT*)P.ids, b * P.ids_sb + (long long)(i - 1) * P.ids_sf,
+                               P.rows[i - 1], P.err);
+  return id < 0 ? nullptr : P.table[i - 1] + id * P.D;
+}
+
+// stage the F1 rows of sample b into xt (row stride RS) with bulk async copies
+template <typename IdT>
+__device__ __forceinline__ void dot_issue_rows(const DotParams& P, long long b, float* xt, int RS,
+                                               uint64_t* bar, int lane) {
+  const int F1 = P.F1, D = P.D;
+  const float* src[2];
+  unsigned nvalid = 0;
+#pragma unroll
+  for (int k = 0; k < 2; ++k) {
+    const int r = lane + 32 * k;
+    src[k] = r < F1 ? dot_src_row<IdT>(P, b, r) : nullptr;
+    if (r < F1 && !src[k])
+      for (int d = 0; d < D; ++d) xt[r * RS + d] = 0.f;  // bad id: row reads as zeros
+    nvalid += __popc(__ballot_sync(0xffffffffu, src[k] != nullptr));
+  }
+  if (lane == 0) mbar_expect_tx(bar, nvalid * (unsigned)D * 4u);
+  __syncwarp();
+#pragma unroll
+  for (int k = 0; k < 2; ++k) {
+    const int r = lane + 32 * k;
+    if (src[k]) bulk_g2s(xt + r * RS, src[k], (unsigned)D * 4u, bar);
+  }
+}
+
+__device__ __forceinline__ void tri_block(int blk, int& bi, int& bj) {
+  // blk -> (bi, bj), bj <= bi, row-major over the lower triangle of blocks
+  int i = (int)((sqrtf(8.f * blk + 1.f) - 1.f) * 0.5f);
+  while ((i + 1) * (i + 2) / 2 <= blk) ++i;
+  while (i * (i + 1) / 2 > blk) --i;
+  bi = i;
+  bj = blk - i * (i + 1) / 2;
+}
+
+template <typename IdT>
+__global__ void __launch_bounds__(512, 1)
+dot_fwd_kernel(const __grid_constant__ DotParams P, int warp_floats) {
+  extern __shared__ __align__(16) float smem[];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
+  const int F1 = P.F1, D = P.D;
+  const int F1p = (F1 + 3) & ~3, nbr = F1p >> 2;
+  const int RS = dot_row_stride(D);
+  const int npairs = F1 * (F1 - 1) / 2;
+  float* xt = smem + (size_t)warp * warp_floats;
+  float* zst = xt + F1p * RS;
+  uint64_t* bar = reinterpret_cast<uint64_t*>(zst + ((npairs + 3) & ~3));
+
+  if (lane == 0) {
+    mbar_init(bar, 1);
+    mbar_fence_init();
+  }
+  for (int i = F1 * RS + lane; i < F1p * RS; i += 32) xt[i] = 0.f;  // pad rows stay zero
+  __syncwarp();
+
+  const long long stride = (long long)gridDim.x * nwarps;
+  long long b = (long long)blockIdx.x * nwarps + warp;
+  uint32_t parity = 0;
+  if (b < P.B) dot_issue_rows<IdT>(P, b, xt, RS, bar, lane);
+  const int nblk = nbr * (nbr + 1) / 2;
+
+  for (; b < P.B; b += stride) {
+    mbar_wait(bar, parity);
+    parity ^= 1;
+    for (int blk = lane; blk < nblk; blk += 32) {
+      int bi, bj;
+      tri_block(blk, bi, bj);
+      // block (bi,bj) covers rows {bi + r*nbr} x {bj + c*nbr}
+      float acc[4][4];
+#pragma unroll
+      for (int r = 0; r < 4; ++r)
+#pragma unroll
+        for (int c = 0; c < 4; ++c) acc[r][c] = 0.f;
+      const float* pa = xt + bi * RS;
+      const float* pb = xt + bj * RS;
+      const int rstep = nbr * RS;
+#pragma unroll 2
+      for (int d = 0; d < D; d += 4) {
+        float4 a[4], q[4];
+#pragma unroll
+        for (int r = 0; r < 4; ++r) {
+          a[r] = *reinterpret_cast<const float4*>(pa + r * rstep + d);
+          q[r] = *reinterpret_cast<const float4*>(pb + r * rstep + d);
+        }
+#pragma unroll
+        for (int r = 0; r < 4; ++r)
+#pragma unroll
+          for (int c = 0; c < 4; ++c) {
+            acc[r][c] = fmaf(a[r].x, q[c].x, acc[r][c]);
+            acc[r][c] = fmaf(a[r].y, q[c].y, acc[r][c]);
+            acc[r][c] = fmaf(a[r].z, q[c].z, acc[r][c]);
+            acc[r][c] = fmaf(a[r].w, q[c].w, acc[r][c]);
+          }
+      }
+#pragma unroll
+      for (int r = 0; r < 4; ++r)
+#pragma unroll
+        for (int c = 0; c < 4; ++c) {
+          const int i = bi + r * nbr, j = bj + c * nbr;
+          if (i < F1 && j < i) zst[i * (i - 1) / 2 + j] = acc[r][c];
+          else if (bi != bj && j < F1 && i < j) zst[j * (j - 1) / 2 + i] = acc[r][c];
+        }
+    }
+    __syncwarp();
+    float* o = P.out + b * P.out_sb;
+    for (int d = lane; d < D; d += 32) o[d] = xt[d];
+    for (int p = lane; p < npairs; p += 32) o[D + p] = zst[p];
+    for (int p = D + npairs + lane; p < P.out_cols; p += 32) o[p] = 0.f;
+    __syncwarp();  // every lane is done reading xt/zst before the next sample overwrites them
+    if (b + stride < P.B) dot_issue_rows<IdT>(P, b + stride, xt, RS, bar, lane);
+  }
+}
+
+// backward: dX[i] = sum_j S[i][j] X[j],  S symmetric from dZ, plus the passthrough on row 0
+template <typename IdT>
+__global__ void __launch_bounds__(512, 1)
+dot_bwd_kernel(const __grid_constant__ DotParams P, int warp_floats) {
+  extern __shared__ __align__(16) float smem[];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
+  const int F1 = P.F1, D = P.D;
+  const int F1p = (F1 + 7) & ~7;  // i-tiles of 8 rows
+  const int RS = dot_row_stride(D);
+  const int npairs = F1 * (F1 - 1) / 2;
+  // CTA-shared pair table, then per-warp regions
+  unsigned short* pair_ij = reinterpret_cast<unsigned short*>(smem);
+  const int pair_floats = ((npairs + 1) / 2 + 3) & ~3;
+  float* wbase = smem + pair_floats + (size_t)warp * warp_floats;
+  float* xt = wbase;                // [F1][RS]
+  float* S = xt + F1 * RS;          // [F1p][F1p]
+  uint64_t* bar = reinterpret_cast<uint64_t*>(S + F1p * F1p);
+
+  for (int p = threadIdx.x; p < npairs; p += blockDim.x) {
+    int i = (int)((1.f + sqrtf(1.f + 8.f * p)) * 0.5f);
+    while (i * (i - 1) / 2 > p) --i;
+    while ((i + 1) * i / 2 <= p) ++i;
+    pair_ij[p] = (unsigned short)((i << 8) | (p - i * (i - 1) / 2));
+  }
+  if (lane == 0) {
+    mbar_init(bar, 1);
+    mbar_fence_init();
+  }
+  for (int i = lane; i < F1p * F1p; i += 32) S[i] = 0.f;  // diagonal and padding stay zero
+  __syncthreads();
+
+  const long long stride = (long long)gridDim.x * nwarps;
+  long long b = (long long)blockIdx.x * nwarps + warp;
+  uint32_t parity = 0;
+  if (b < P.B) dot_issue_rows<IdT>(P, b, xt, RS, bar, lane);
+
+  for (; b < P.B; b += stride) {
+    const float* g = P.gout + b * P.gout_sb;
+    for (int p = lane; p < npairs; p += 32) {
+      const float v = __ldg(g + D + p);
+      const int ij = pair_ij[p];
+      const int i = ij >> 8, j = ij & 255;
+      S[i * F1p + j] = v;
+      S[j * F1p + i] = v;
+    }
+    __syncwarp();
+    mbar_wait(bar, parity);
+    parity ^= 1;
+    for (int d0 = lane * 4; d0 < D; d0 += 128) {
+      for (int i0 = 0; i0 < F1; i0 += 8) {
+        float4 acc[8];
+#pragma unroll
+        for (int r = 0; r < 8; ++r) acc[r] = make_float4(0.f, 0.f, 0.f, 0.f);
+        for (int j = 0; j < F1; ++j) {
+          const float4 xj = *reinterpret_cast<const float4*>(xt + j * RS + d0);
+          const float4 s0 = *reinterpret_cast<const float4*>(S + j * F1p + i0);
+          const float4 s1 = *reinterpret_cast<const float4*>(S + j * F1p + i0 + 4);
+          const float s[8] = {s0.x, s0.y, s0.z, s0.w, s1.x, s1.y, s1.z, s1.w};
+#pragma unroll
+          for (int r = 0; r < 8; ++r) {
+            acc[r].x = fmaf(s[r], xj.x, acc[r].x);
+            acc[r].y = fmaf(s[r], xj.y, acc[r].y);
+            acc[r].z = fmaf(s[r], xj.z, acc[r].z);
+            acc[r].w = fmaf(s[r], xj.w, acc[r].w);
+          }
+        }
+#pragma unroll
+        for (int r = 0; r < 8; ++r) {
+          const int i = i0 + r;
+          if (i < F1) {
+            float4 v = acc[r];
+            float* dst;
+            if (P.gx) {
+              dst = P.gx + (b * F1 + i) * (long long)D + d0;
+            } else if (i == 0) {
+              dst = P.gdense + b * P.gdense_sb + d0;
+            } else {
+              dst = P.gemb + b * P.gemb_sb + (long long)(i - 1) * D + d0;
+            }
+            if (i == 0) {  // out[:, :D] is X[0] itself
+              v.x += __ldg(g + d0);
+              v.y += __ldg(g + d0 + 1);
+              v.z += __ldg(g + d0 + 2);
+              v.w += __ldg(g + d0 + 3);
+            }
+            *reinterpret_cast<float4*>(dst) = v;
+          }
+        }
+      }
+    }
+    __syncwarp();
+    if (b + stride < P.B) dot_issue_rows<IdT>(P, b + stride, xt, RS, bar, lane);
+  }
+}
+
+static int dot_check_common(long long B, int F1, int D) {
+  if (B < 0 || F1 < 2 || D <= 0) return RTF_E_ARG;
+  if (F1 > RTF_MAX_FIELDS || D % 4 || D > 1024) return RTF_E_RANGE;
+  return 0;
+}
+
+template <typename Kern>
+static int dot_launch(Kern kern, const DotParams& P, int warp_floats, int cta_floats,
+                      cudaStream_t st) {
+  const size_t max_smem = 227 * 1024;
+  const size_t per_warp = (size_t)warp_floats * 4;
+  int nwarps = (int)((max_smem - (size_t)cta_floats * 4) / per_warp);
+  if (nwarps < 1) return RTF_E_RANGE;
+  if (nwarps > 16) nwarps = 16;
+  const size_t smem = (size_t)cta_floats * 4 + per_warp * nwarps;
+  cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  if (e != cudaSuccess) return (int)e;
+  long long blocks = (P.B + nwarps - 1) / nwarps;
+  if (blocks > kNumSMs) blocks = kNumSMs;  // persistent: one CTA per SM
+  kern<<<(unsigned)blocks, nwarps * 32, smem, st>>>(P, warp_floats);
+  RTF_CHECK_LAUNCH();
+  return 0;
+}
+
+static int dot_fwd_impl(DotParams& P, int ids_i64, cudaStream_t st) {
+  const int F1p = (P.F1 + 3) & ~3, RS = dot_row_stride(P.D);
+  const int npairs = P.F1 * (P.F1 - 1) / 2;
+  const int warp_floats = F1p * RS + ((npairs + 3) & ~3) + 4;  // + mbarrier (8 B, 16-B slot)
+  return ids_i64 ? dot_launch(dot_fwd_kernel<int64_t>, P, warp_floats, 0, st)
+                 : dot_launch(dot_fwd_kernel<int32_t>, P, warp_floats, 0, st);
+}
+static int dot_bwd_impl(DotParams& P, int ids_i64, cudaStream_t st) {
+  const int F1p = (P.F1 + 7) & ~7, RS = dot_row_stride(P.D);
+  const int npairs = P.F1 * (P.F1 - 1) / 2;
+  const int warp_floats = P.F1 * RS + F1p * F1p + 4;
+  const int cta_floats = ((npairs + 1) / 2 + 3) & ~3;
+  return ids_i64 ? dot_launch(dot_bwd_kernel<int64_t>, P, warp_floats, cta_floats, st)
+                 : dot_launch(dot_bwd_kernel<int32_t>, P, warp_floats, cta_floats, st);
+}
+
+static int dot_fill_tables(DotParams& P, const float* const* tables, const int64_t* rows,
+                           int n_fields) {
+  for (int f = 0; f < n_fields; ++f) {
+    if (!tables[f] || rows[f] <= 0) return RTF_E_ARG;
+    if ((uintptr_t)tables[f] % 16) return RTF_E_ALIGN;
+    P.table[f] = tables[f];
+    P.rows[f] = rows[f];
+  }
+  return 0;
+}
+
+}  // namespace rtf
+
+using namespace rtf;
+
+extern "C" int rtf_dot_interact_fwd(const float* d_x, int64_t B, int F1, int D, float* d_out,
+                                    int64_t out_sb, int out_cols, void* stream) {
+  int rc = dot_check_common(B, F1, D);
+  if (rc) return rc;
+  if (B == 0) return 0;
+  if (!d_x || !d_out) return RTF_E_ARG;
+  const int need = D + F1 * (F1 - 1) / 2;
+  if (out_cols < need || out_sb < out_cols) return RTF_E_ARG;
+  if ((uintptr_t)d_x % 16) return RTF_E_ALIGN;
+  DotParams P = {};
+  P.x = d_x; P.B = B; P.F1 = F1; P.D = D; P.out = d_out; P.out_sb = out_sb; P.out_cols = out_cols;
+  return dot_fwd_impl(P, 0, (cudaStream_t)stream);
+}
+
+extern "C" int rtf_dot_interact_bwd(const float* d_x, const float* d_gout, int64_t gout_sb,
+                                    int64_t B, int F1, int D, float* d_gx, void* stream) {
+  int rc = dot_check_common(B, F1, D);
+  if (rc) return rc;
+  if (B == 0) return 0;
+  if (!d_x || !d_gout || !d_gx) return RTF_E_ARG;
+  if (gout_sb < D + F1 * (F1 - 1) / 2) return RTF_E_ARG;
+  if ((uintptr_t)d_x % 16 || (uintptr_t)d_gx % 16) return RTF_E_ALIGN;
+  DotParams P = {};
+  P.x = d_x; P.B = B; P.F1 = F1; P.D = D; P.gout = d_gout; P.gout_sb = gout_sb; P.gx = d_gx;
+  return dot_bwd_impl(P, 0, (cudaStream_t)stream);
+}
+
+extern "C" int rtf_embed_dot_fwd(const float* const* tables, const int64_t* rows, int n_fields,
+                                 int D, const void* d_ids, int ids_i64, int64_t B, int64_t ids_sb,
+                                 int64_t ids_sf, const float* d_dense, int64_t dense_sb,
+                                 float* d_out, int64_t out_sb, int out_cols, int32_t* d_err,
+                                 void* stream) {
+  if (!tables || !rows || n_fields < 1) return RTF_E_ARG;
+  const int F1 = n_fields + 1;
+  int rc = dot_check_common(B, F1, D);
+  if (rc) return rc;
+  if (B == 0) return 0;
+  if (!d_ids || !d_dense || !d_out) return RTF_E_ARG;
+  const int need = D + F1 * (F1 - 1) / 2;
+  if (out_cols < need || out_sb < out_cols) return RTF_E_ARG;
+  if ((uintptr_t)d_dense % 16 || dense_sb % 4) return RTF_E_ALIGN;
+  DotParams P = {};
+  rc = dot_fill_tables(P, tables, rows, n_fields);
+  if (rc) return rc;
+  P.ids = d_ids; P.ids_sb = ids_sb; P.ids_sf = ids_sf; P.dense = d_dense; P.dense_sb = dense_sb;
+  P.B = B; P.F1 = F1; P.D = D; P.out = d_out; P.out_sb = out_sb; P.out_cols = out_cols;
+  P.err = d_err;
+  return dot_fwd_impl(P, ids_i64, (cudaStream_t)stream);
+}
+
+extern "C" int rtf_embed_dot_bwd(const float* const* tables, const int64_t* rows, int n_fields,
+                                 int D, const void* d_ids, int ids_i64, int64_t B, int64_t ids_sb,
+                                 int64_t ids_sf, const float* d_dense, int64_t dense_sb,
+                                 const float* d_gout, int64_t gout_sb, float* d_gdense,
+                                 int64_t gdense_sb, float* d_gemb, int64_t gemb_sb, void* stream) {
+  if (!tables || !rows || n_fields < 1) return RTF_E_ARG;
+  const int F1 = n_fields + 1;
+  int rc = dot_check_common(B, F1, D);
+  if (rc) return rc;
+  if (B == 0) return 0;
+  if (!d_ids || !d_dense || !d_gout || !d_gdense || !d_gemb) return RTF_E_ARG;
+  if (gout_sb < D + F1 * (F1 - 1) / 2 || gemb_sb < (int64_t)n_fields * D) return RTF_E_ARG;
+  if ((uintptr_t)d_dense % 16 || dense_sb % 4 || (uintptr_t)d_gdense % 16 || gdense_sb % 4 ||
+      (uintptr_t)d_gemb % 16 || gemb_sb % 4)
+    return RTF_E_ALIGN;
+  DotParams P = {};
+  rc = dot_fill_tables(P, tables, rows, n_fields);
+  if (rc) return rc;
+  P.ids = d_ids; P.ids_sb = ids_sb; P.ids_sf = ids_sf; P.dense = d_dense; P.dense_sb = dense_sb;
+  P.B = B; P.F1 = F1; P.D = D; P.gout = d_gout; P.gout_sb = gout_sb; P.gdense = d_gdense;
+  P.gdense_sb = gdense_sb; P.gemb = d_gemb; P.gemb_sb = gemb_sb;
+  return dot_bwd_impl(P, ids_i64, (cudaStream_t)stream);
+}

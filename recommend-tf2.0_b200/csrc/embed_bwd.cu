@@ -596,9 +596,9 @@ extern "C" int rtf_embed_bwd(float* const* weights, float* const* state1, float*
                              int32_t* d_num_uniq, int* row_bits_out, void* d_workspace,
                              size_t workspace_bytes, void* stream) {
   using namespace rtf;
-  if (!weights || !rows || !dims || !field_table || !d_ids || !d_grad || !opt || !d_workspace)
-    return RTF_E_ARG;
+  if (!weights || !rows || !dims || !field_table || !opt) return RTF_E_ARG;
   if (n_tables <= 0 || n_fields <= 0 || B < 0 || L <= 0) return RTF_E_ARG;
+  if (B > 0 && (!d_ids || !d_grad || !d_workspace)) return RTF_E_ARG;
   if (n_tables > RTF_MAX_FIELDS || n_fields > RTF_MAX_FIELDS) return RTF_E_RANGE;
   if (pool < RTF_POOL_NONE || pool > RTF_POOL_MEAN) return RTF_E_ARG;
   if (opt->kind < RTF_OPT_NONE || opt->kind > RTF_OPT_ADAM) return RTF_E_ARG;

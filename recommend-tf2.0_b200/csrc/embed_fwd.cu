@@ -230,10 +230,11 @@ extern "C" int rtf_embed_fwd(const float* const* tables, const int64_t* rows,
                              int pool, float* d_out, int64_t out_sb, int32_t* d_err,
                              void* stream) {
   using namespace rtf;
-  if (!tables || !rows || !dims || !d_ids || !d_out) return RTF_E_ARG;
+  if (!tables || !rows || !dims) return RTF_E_ARG;
   if (n_fields <= 0 || B < 0 || L <= 0) return RTF_E_ARG;
   if (pool < RTF_POOL_NONE || pool > RTF_POOL_MEAN) return RTF_E_ARG;
-  if (B == 0) return 0;
+  if (B == 0) return 0;  // empty batch: nothing to read or write
+  if (!d_ids || !d_out) return RTF_E_ARG;
   long long sumD = 0;
   for (int f = 0; f < n_fields; ++f) {
     if (!tables[f] || rows[f] <= 0 || dims[f] <= 0) return RTF_E_ARG;

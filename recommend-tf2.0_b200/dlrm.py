@@ -1,0 +1,78 @@
+"""DLRM with the reference's constructor (src/ctr/dlrm/model.py:16-40) on the B200 kernels.
+
+The reference's `call` is broken (`self.dense_inputs`, `self.dnn_network` do not exist, :44,50)
+and concatenates where the paper it cites interacts (:48).  `interaction='dot'` (default) is
+the paper's pairwise dot through the fused gather+interaction kernel; `interaction='cat'`
+reproduces line 48 literally.  Dense MLPs are framework GEMMs (fp32); embeddings, interaction,
+their backward and the sparse optimizer are librtf_b200 kernels.
+"""
+from __future__ import annotations
+
+from typing import Optional, Sequence
+
+import torch
+
+from .embedding import EmbeddingTables, SparseOptimizer
+from .interaction import dot_out_cols, embed_dot
+from .layers.core import DNN, Dense, Layer, binary_crossentropy
+
+
+class DLRM(Layer):
+    def __init__(self, feature_columns, bot_dnn_hidden_units=(64, 32, 16),
+                 top_dnn_hidden_units=(128, 64), activation="relu", dnn_dropout=0.0,
+                 embed_reg=1e-4, interaction: str = "dot",
+                 sparse_optimizer: Optional[SparseOptimizer] = None, pad_to: int = 1,
+                 input_bn: bool = True, seed: Optional[int] = None):
+        super().__init__()
+        self.dense_feature_columns, self.sparse_feature_columns = feature_columns
+        self.interaction, self.pad_to, self.embed_reg = interaction, pad_to, embed_reg
+        rows = [f["feat_num"] for f in self.sparse_feature_columns]
+        dims = [f["embed_dim"] for f in self.sparse_feature_columns]
+        if interaction == "dot" and (len(set(dims)) != 1 or bot_dnn_hidden_units[-1] != dims[0]):
+            raise ValueError("dot interaction needs equal embed_dim == bot_dnn_hidden_units[-1]")
+        # 'random_uniform' + l2(embed_reg) as at model.py:31-35
+        self.embed_layers = EmbeddingTables(rows, dims, "random_uniform",
+                                            optimizer=sparse_optimizer, seed=seed)
+        self.bot_dnn = DNN(bot_dnn_hidden_units, activation, dnn_dropout, input_bn=input_bn)
+        self.top_dnn = DNN(top_dnn_hidden_units, activation, dnn_dropout, input_bn=input_bn)
+        self.final_dense = Dense(1, activation=None)
+
+    def call(self, inputs, **kwargs):
+        dense_inputs, sparse_inputs = inputs
+        dense_fea = self.bot_dnn(dense_inputs)
+        if self.interaction == "cat":
+            sparse_embed = self.embed_layers.lookup(sparse_inputs)
+            x = torch.cat([sparse_embed, dense_fea], dim=-1)
+        else:
+            x = embed_dot(self.embed_layers, sparse_inputs, dense_fea, pad_to=self.pad_to)
+        top = self.final_dense(self.top_dnn(x))
+        return torch.sigmoid(top)
+
+    def dense_parameters(self):
+        emb = {id(p) for p in self.embed_layers.parameters()}
+        return [p for p in self.parameters() if id(p) not in emb]
+
+
+class DLRMTrainer:
+    """One training step = forward, Keras BCE, backward (K4 bwd -> K2 with the fused sparse
+    optimizer on the tables), dense Adam on the MLPs (Keras eps 1e-7)."""
+
+    def __init__(self, model: DLRM, lr: float = 1e-3):
+        self.model = model
+        if model.embed_layers.optimizer is None:
+            model.embed_layers.set_optimizer(SparseOptimizer("adam", lr=lr, l2=model.embed_reg))
+        self.dense_opt = None
+        self.lr = lr
+
+    def step(self, dense, sparse, labels) -> torch.Tensor:
+        m = self.model
+        m.embed_layers.begin_step()
+        pred = m([dense, sparse])
+        if self.dense_opt is None:  # layers build on first call
+            self.dense_opt = torch.optim.Adam(m.dense_parameters(), lr=self.lr, eps=1e-7,
+                                              fused=dense.is_cuda)
+        loss = binary_crossentropy(labels, pred)
+        self.dense_opt.zero_grad(set_to_none=True)
+        loss.backward()
+        self.dense_opt.step()
+        return loss.detach()

@@ -162,22 +162,9 @@ class _LookupFn(torch.autograd.Function):
 
     @staticmethod
     def backward(ctx, grad):
-        tset = ctx.tset
-        grad = grad.contiguous()
-        nw = len(tset.weights)
-        if tset.optimizer is not None:
-            tset.apply_sparse_grad(ctx.ids, ctx.field_table, grad, ctx.layout, ctx.pool)
-            return (None,) * 5 + (None,) * nw
-        keys, g, row_bits = embed_bwd(tset.weights, ctx.field_table, ctx.ids, grad, ctx.layout,
-                                      ctx.pool, want_unique=True)
-        tab = keys >> row_bits
-        row = keys & ((1 << row_bits) - 1)
-        grads = []
-        for t, w in enumerate(tset.weights):
-            sel = tab == t
-            grads.append(torch.sparse_coo_tensor(row[sel].unsqueeze(0), g[sel][:, : w.shape[1]],
-                                                 size=w.shape).coalesce())
-        return (None,) * 5 + tuple(grads)
+        grads = ctx.tset.grads_from_lookup_grad(ctx.ids, ctx.field_table, grad.contiguous(),
+                                                ctx.layout, ctx.pool)
+        return (None,) * 5 + grads
 
 
 class EmbeddingTables(torch.nn.Module):
@@ -190,10 +177,11 @@ class EmbeddingTables(torch.nn.Module):
         device = torch.device("cuda" if device is None else device)
         gen = None
         if seed is not None:
-            gen = torch.Generator(device="cpu").manual_seed(seed)
+            gen = torch.Generator(device=device).manual_seed(seed)
         self.weights = torch.nn.ParameterList()
         for n, d in zip(rows, dims):
-            w = torch.empty((int(n), int(d)), dtype=torch.float32)
+            # initialised in place in HBM (a Criteo-sized table set is tens of GB)
+            w = torch.empty((int(n), int(d)), dtype=torch.float32, device=device)
             if initializer == "random_uniform":      # Keras: U(-0.05, 0.05)
                 w.uniform_(-0.05, 0.05, generator=gen)
             elif initializer == "random_normal":     # Keras: N(0, 0.05^2)
@@ -202,7 +190,7 @@ class EmbeddingTables(torch.nn.Module):
                 w.zero_()
             else:
                 raise ValueError(f"unknown initializer {initializer!r}")
-            self.weights.append(torch.nn.Parameter(w.to(device)))
+            self.weights.append(torch.nn.Parameter(w))
         self.register_buffer("err", torch.zeros(1, dtype=torch.int32, device=device))
         self.optimizer = None
         self.state1: List[Optional[torch.Tensor]] = []
@@ -232,6 +220,24 @@ class EmbeddingTables(torch.nn.Module):
         step = max(opt.step, 1)
         embed_bwd([w.data for w in self.weights], field_table, ids, grad, layout, pool,
                   opt=opt.struct_for_step(step), state1=self.state1, state2=self.state2)
+
+    def grads_from_lookup_grad(self, ids, field_table, grad, layout="BF", pool=None):
+        """Backward of a lookup given d(out): with a fused optimizer the touched rows are
+        updated in place (returns Nones); otherwise returns one sparse COO gradient per table."""
+        nw = len(self.weights)
+        if self.optimizer is not None:
+            self.apply_sparse_grad(ids, field_table, grad, layout, pool)
+            return (None,) * nw
+        keys, g, row_bits = embed_bwd(list(self.weights), field_table, ids, grad, layout, pool,
+                                      want_unique=True)
+        tab = keys >> row_bits
+        row = keys & ((1 << row_bits) - 1)
+        grads = []
+        for t, w in enumerate(self.weights):
+            sel = tab == t
+            grads.append(torch.sparse_coo_tensor(row[sel].unsqueeze(0), g[sel][:, : w.shape[1]],
+                                                 size=w.shape, check_invariants=False).coalesce())
+        return tuple(grads)
 
     def check_ids(self):
         """Raise like TF's CPU gather (InvalidArgument) if any lookup since the last check used an
