@@ -125,6 +125,50 @@ int rtf_embed_dot_bwd(const float* const* tables, const int64_t* rows, int n_fie
                       int64_t gout_sb, float* d_gdense, int64_t gdense_sb, float* d_gemb,
                       int64_t gemb_sb, void* stream);
 
+/* ---- deterministic column sum: out[c] = sum_b rowscale[b] * x[b,c] (rowscale may be NULL) ---
+ * the batch-wide reductions of weight gradients (FM w, dense FM rows, attention projections);
+ * replaces the atomics-based reductions TF uses for MatMul/BiasAdd gradients.              */
+int rtf_colsum_workspace(int64_t B, int cols, size_t* bytes);
+int rtf_colsum(const float* d_x, int64_t x_sb, const float* d_rowscale, int64_t B, int cols,
+               float* d_out, void* d_ws, void* stream);
+
+/* ---- K3a: FM layer -------------------------------------------------------------------
+ * replaces: ctr.layers.modules.FM.call  src/ctr/layers/modules.py:57-72
+ * first (B,P1), w (P1), second (B,F,D) [the 2-D tensor DeepFM passes is F=M, D=1].
+ *   first_batch_scalar=1, sum_d=0 : reference semantics — first order summed over the WHOLE
+ *       batch (:65), out (B*D) = first + 0.5*((sum_f x)^2 - sum_f x^2)[b,d]
+ *   first_batch_scalar=0          : per-sample first order (paper);  sum_d=1 also sums the
+ *       second order over d -> out (B).
+ * _bwd writes d_gfirst (B,P1) / d_gw (P1) / d_gsecond (B,F,D); any may be NULL.           */
+int rtf_fm_layer_workspace(int64_t B, int P1, size_t* bytes);
+int rtf_fm_layer_fwd(const float* d_first, int64_t first_sb, const float* d_w, int P1,
+                     const float* d_second, int64_t second_sb, int F, int D, int64_t B,
+                     int first_batch_scalar, int sum_d, float* d_out, void* d_ws, void* stream);
+int rtf_fm_layer_bwd(const float* d_first, int64_t first_sb, const float* d_w, int P1,
+                     const float* d_second, int64_t second_sb, int F, int D, int64_t B,
+                     int first_batch_scalar, int sum_d, const float* d_gout, float* d_gfirst,
+                     int64_t gfirst_sb, float* d_gw, float* d_gsecond, int64_t gsecond_sb,
+                     void* d_ws, void* stream);
+
+/* ---- K3b: FM model in gather form ------------------------------------------------------
+ * replaces: ctr.fm.model.FM.call  src/ctr/fm/model.py:34-53 (dense one-hot (B,M) @ w, @ V^T)
+ * Every feature owns one row of kp floats: columns [0,k) = its column of V, column k = its
+ * w, the rest zero padding.  tables[f] (N_f,kp) for the sparse fields, d_dense_table
+ * (n_dense,kp) for the dense features (scaled by their value x).
+ *   A_c = sum_i x_i R_i[c];  out = sigmoid(w0 + A_k + 0.5 * sum_{c<k} (A_c^2 - sum_i x_i^2 R_i[c]^2))
+ * _fwd saves A (B,kp).  _bwd writes per-sample gradient rows: d_gsparse (B, n_fields*kp) —
+ * K2's d_grad — and d_gdense_rows (B, n_dense*kp) (column-sum it), and d_dz (B) (sum = dw0). */
+int rtf_fm_gather_fwd(const float* const* tables, const int64_t* rows, int n_fields, int k,
+                      int kp, const float* d_dense_table, int n_dense, const float* d_dense,
+                      int64_t dense_sb, const void* d_ids, int ids_i64, int64_t B, int64_t ids_sb,
+                      int64_t ids_sf, const float* d_w0, float* d_out, float* d_A, int32_t* d_err,
+                      void* stream);
+int rtf_fm_gather_bwd(const float* const* tables, const int64_t* rows, int n_fields, int k,
+                      int kp, const float* d_dense_table, int n_dense, const float* d_dense,
+                      int64_t dense_sb, const void* d_ids, int ids_i64, int64_t B, int64_t ids_sb,
+                      int64_t ids_sf, const float* d_out, const float* d_A, const float* d_gout,
+                      float* d_gsparse, float* d_gdense_rows, float* d_dz, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

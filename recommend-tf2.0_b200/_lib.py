@@ -49,6 +49,16 @@ SIGNATURES = {
                           _int, _p, _p],
     "rtf_embed_dot_bwd": [_p, _p, _int, _int, _p, _int, _i64, _i64, _i64, _p, _i64, _p, _i64,
                           _p, _i64, _p, _i64, _p],
+    "rtf_colsum_workspace": [_i64, _int, C.POINTER(C.c_size_t)],
+    "rtf_colsum": [_p, _i64, _p, _i64, _int, _p, _p, _p],
+    "rtf_fm_layer_workspace": [_i64, _int, C.POINTER(C.c_size_t)],
+    "rtf_fm_layer_fwd": [_p, _i64, _p, _int, _p, _i64, _int, _int, _i64, _int, _int, _p, _p, _p],
+    "rtf_fm_layer_bwd": [_p, _i64, _p, _int, _p, _i64, _int, _int, _i64, _int, _int, _p, _p,
+                         _i64, _p, _p, _i64, _p, _p],
+    "rtf_fm_gather_fwd": [_p, _p, _int, _int, _int, _p, _int, _p, _i64, _p, _int, _i64, _i64,
+                          _i64, _p, _p, _p, _p, _p],
+    "rtf_fm_gather_bwd": [_p, _p, _int, _int, _int, _p, _int, _p, _i64, _p, _int, _i64, _i64,
+                          _i64, _p, _p, _p, _p, _p, _p, _p],
 }
 
 _lib = None

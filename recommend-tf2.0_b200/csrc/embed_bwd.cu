@@ -199,33 +199,44 @@ static int exclusive_scan(In in, Out out, long long n, uint32_t* tile_sums, cuda
 }
 
 // ------------------------------------------------------------------ 2. radix sort
+// LSD, stable.  The digit width is chosen per call (<= SORT_MAX_BITS) so that the significant
+// key bits take the fewest passes: 29 bits (Criteo: 24 row bits + 5 table bits) = 3 passes of 10.
 constexpr int SORT_THREADS = 256;
 constexpr int SORT_WARPS = SORT_THREADS / 32;
 constexpr int SORT_ITEMS = 16;
 constexpr int SORT_TILE = SORT_THREADS * SORT_ITEMS;  // 4096 keys per CTA; a warp owns 512 contiguous
+constexpr int SORT_MAX_BITS = 10;
+constexpr int SORT_MAX_BINS = 1 << SORT_MAX_BITS;
 
 __global__ void __launch_bounds__(SORT_THREADS)
-sort_hist(const uint32_t* __restrict__ keys, long long n, int shift, uint32_t* __restrict__ hist,
-          int nblk) {
-  __shared__ uint32_t sh[256];
-  sh[threadIdx.x] = 0;
+sort_hist(const uint32_t* __restrict__ keys, long long n, int shift, int bits,
+          uint32_t* __restrict__ hist, int nblk) {
+  __shared__ uint32_t sh[SORT_MAX_BINS];
+  const int bins = 1 << bits;
+  const uint32_t mask = (uint32_t)bins - 1u;
+  for (int i = threadIdx.x; i < bins; i += SORT_THREADS) sh[i] = 0;
   __syncthreads();
   const long long base = (long long)blockIdx.x * SORT_TILE;
 #pragma unroll
   for (int r = 0; r < SORT_ITEMS; ++r) {
     const long long i = base + r * SORT_THREADS + threadIdx.x;
-    if (i < n) atomicAdd(&sh[(keys[i] >> shift) & 255u], 1u);
+    if (i < n) atomicAdd(&sh[(keys[i] >> shift) & mask], 1u);
   }
   __syncthreads();
-  hist[(long long)threadIdx.x * nblk + blockIdx.x] = sh[threadIdx.x];  // digit-major
+  for (int d = threadIdx.x; d < bins; d += SORT_THREADS)
+    hist[(long long)d * nblk + blockIdx.x] = sh[d];  // digit-major
 }
 
 __global__ void __launch_bounds__(SORT_THREADS)
 sort_scatter(const uint32_t* __restrict__ keys_in, const uint32_t* __restrict__ vals_in,
              uint32_t* __restrict__ keys_out, uint32_t* __restrict__ vals_out, long long n,
-             int shift, const uint32_t* __restrict__ hist_scanned, int nblk, int iota_vals) {
-  __shared__ uint32_t whist[SORT_WARPS][256];
-  for (int i = threadIdx.x; i < SORT_WARPS * 256; i += SORT_THREADS) (&whist[0][0])[i] = 0;
+             int shift, int bits, const uint32_t* __restrict__ hist_scanned, int nblk,
+             int iota_vals) {
+  __shared__ uint32_t whist[SORT_WARPS][SORT_MAX_BINS];
+  const int bins = 1 << bits;
+  const uint32_t mask = (uint32_t)bins - 1u;
+  for (int i = threadIdx.x; i < SORT_WARPS * SORT_MAX_BINS; i += SORT_THREADS)
+    (&whist[0][0])[i] = 0;
   __syncthreads();
   const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
   const uint32_t lt_mask = (1u << lane) - 1u;
@@ -240,7 +251,7 @@ sort_scatter(const uint32_t* __restrict__ keys_in, const uint32_t* __restrict__ 
     const uint32_t vmask = __ballot_sync(0xffffffffu, valid);
     rank[r] = 0;
     if (valid) {
-      const uint32_t d = (k[r] >> shift) & 255u;
+      const uint32_t d = (k[r] >> shift) & mask;
       const uint32_t m = __match_any_sync(vmask, d);
       const uint32_t prior = whist[wid][d];
       __syncwarp(vmask);
@@ -250,8 +261,8 @@ sort_scatter(const uint32_t* __restrict__ keys_in, const uint32_t* __restrict__ 
     }
   }
   __syncthreads();
-  {  // thread d turns per-warp counts into global bases (warps in index order => stable)
-    const int d = threadIdx.x;
+  // per-warp counts -> global bases (warps in index order => stable)
+  for (int d = threadIdx.x; d < bins; d += SORT_THREADS) {
     uint32_t run = hist_scanned[(long long)d * nblk + blockIdx.x];
 #pragma unroll
     for (int w = 0; w < SORT_WARPS; ++w) {
@@ -265,7 +276,7 @@ sort_scatter(const uint32_t* __restrict__ keys_in, const uint32_t* __restrict__ 
   for (int r = 0; r < SORT_ITEMS; ++r) {
     const long long i = wbase + r * 32 + lane;
     if (i < n) {
-      const uint32_t d = (k[r] >> shift) & 255u;
+      const uint32_t d = (k[r] >> shift) & mask;
       const uint32_t pos = whist[wid][d] + rank[r];
       keys_out[pos] = k[r];
       vals_out[pos] = v[r];
@@ -511,7 +522,7 @@ seg_combine(const __grid_constant__ BwdParams P, const __grid_constant__ SegWork
   for (int k = 0; k < VPL; ++k)
 #pragma unroll
     for (int e = 0; e < VEC; ++e) acc[k].v[e] = 0.f;
-  constexpr int U = 4;
+  constexpr int U = VPL == 1 ? 16 : 4;  // partials are contiguous and L2-resident: go deep
   for (uint32_t c0 = 0; c0 < nch; c0 += U) {
     Vec<VEC> x[U][VPL];
 #pragma unroll
@@ -567,8 +578,8 @@ static WsLayout ws_layout(long long n, int dim_max) {
   w.keys1 = take(nn * 4);
   w.vals0 = take(nn * 4);
   w.vals1 = take(nn * 4);
-  w.hist = take(256 * nblk * 4);
-  const size_t scan_n = nn > 256 * nblk ? nn : 256 * nblk;
+  w.hist = take((size_t)SORT_MAX_BINS * nblk * 4);
+  const size_t scan_n = nn > (size_t)SORT_MAX_BINS * nblk ? nn : (size_t)SORT_MAX_BINS * nblk;
   w.tile_sums = take(((scan_n + SCAN_TILE - 1) / SCAN_TILE + 1) * 4);
   w.seg_start = take((nn + 1) * 4);
   w.counters = take(16);
@@ -682,12 +693,15 @@ extern "C" int rtf_embed_bwd(float* const* weights, float* const* state1, float*
   const int nblk = (int)((n + SORT_TILE - 1) / SORT_TILE);
   const int total_bits = row_bits + table_bits;
   int cur = 0;
-  for (int shift = 0, pass = 0; shift < total_bits; shift += 8, ++pass) {
-    sort_hist<<<nblk, SORT_THREADS, 0, st>>>(keys[cur], n, shift, hist, nblk);
-    int rc = exclusive_scan(InArray{hist}, OutArray{hist}, 256LL * nblk, tile_sums, st);
+  const int npass = (total_bits + SORT_MAX_BITS - 1) / SORT_MAX_BITS;
+  const int bits = (total_bits + npass - 1) / npass;
+  for (int shift = 0, pass = 0; pass < npass; shift += bits, ++pass) {
+    sort_hist<<<nblk, SORT_THREADS, 0, st>>>(keys[cur], n, shift, bits, hist, nblk);
+    int rc = exclusive_scan(InArray{hist}, OutArray{hist}, (long long)(1 << bits) * nblk, tile_sums, st);
     if (rc) return rc;
     sort_scatter<<<nblk, SORT_THREADS, 0, st>>>(keys[cur], vals[cur], keys[cur ^ 1],
-                                                vals[cur ^ 1], n, shift, hist, nblk, pass == 0);
+                                                vals[cur ^ 1], n, shift, bits, hist, nblk,
+                                                pass == 0);
     RTF_CHECK_LAUNCH();
     cur ^= 1;
   }

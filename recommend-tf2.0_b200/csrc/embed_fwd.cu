@@ -37,27 +37,47 @@ embed_fwd_vec(const __grid_constant__ FwdFields P, const IdT* __restrict__ ids, 
   const int F = P.n_fields;
 
   if (pool == RTF_POOL_NONE) {
+    // a group owns U consecutive (b, l, f) items: one decode (a 32-bit division whenever the
+    // item count allows — the emulated 64-bit one cost ~100 issue slots per row), then steps
     const long long LF = (long long)L * F;
     const long long n_items = B * LF;
+    const long long it0 = gid * U;
+    if (it0 >= n_items) return;
+    long long b;
+    int l, f;
+    if (n_items < 0x7fffffffLL) {
+      const unsigned q = (unsigned)it0 / (unsigned)LF;
+      const unsigned r = (unsigned)it0 - q * (unsigned)LF;
+      b = q;
+      l = (int)(r / (unsigned)F);
+      f = (int)(r - (unsigned)l * (unsigned)F);
+    } else {
+      b = it0 / LF;
+      const int r = (int)(it0 - b * LF);
+      l = r / F;
+      f = r - l * F;
+    }
     const float* src[U];
     float* dst[U];
     int nv[U];
 #pragma unroll
     for (int u = 0; u < U; ++u) {
-      const long long it = gid + (long long)u * n_groups;
       src[u] = nullptr;
       dst[u] = nullptr;
       nv[u] = 0;
-      if (it < n_items) {
-        const long long b = it / LF;
-        const int r = (int)(it - b * LF);
-        const int l = r / F;
-        const int f = r - l * F;
+      if (it0 + u < n_items) {
         const long long id = load_id(ids, b * sb + (long long)(P.field0 + f) * sf + l * sl,
                                      P.rows[f], err);
         nv[u] = P.dim[f] >> 2;
         if (id >= 0) src[u] = P.table[f] + id * P.dim[f];
         dst[u] = out + b * out_sb + (long long)l * P.sumD + P.off[f];
+        if (++f == F) {
+          f = 0;
+          if (++l == L) {
+            l = 0;
+            ++b;
+          }
+        }
       }
     }
     float4 v[U][VPL];
