@@ -109,6 +109,17 @@ int rtf_dot_interact_fwd(const float* d_x, int64_t B, int F1, int D, float* d_ou
 int rtf_dot_interact_bwd(const float* d_x, const float* d_gout, int64_t gout_sb, int64_t B,
                          int F1, int D, float* d_gx, void* stream);
 
+/* Same interaction with the F1 rows of a sample addressed one by one: row i of sample b is
+ * row_base[i] + b*row_stride[i] (HOST arrays of F1 device pointers / element strides).  Used
+ * by the multi-GPU path to interact straight out of the all-to-all receive buffer (blocks
+ * ordered by source rank) and to write dX rows into the send buffer of the backward
+ * exchange, with no permute copy.                                            */
+int rtf_dot_rows_fwd(const float* const* row_base, const int64_t* row_stride, int F1, int D,
+                     int64_t B, float* d_out, int64_t out_sb, int out_cols, void* stream);
+int rtf_dot_rows_bwd(const float* const* row_base, const int64_t* row_stride, int F1, int D,
+                     int64_t B, const float* d_gout, int64_t gout_sb, float* const* grad_base,
+                     const int64_t* grad_stride, void* stream);
+
 /* ---- K1+K4 fused: gather the F embedding rows of a sample straight into shared memory
  * (one TMA bulk copy per row), append the bottom-MLP row, interact, write (B, out_cols).
  * replaces: src/ctr/dlrm/model.py:45-48 (lookup + concat + interaction) in one launch.
@@ -168,6 +179,76 @@ int rtf_fm_gather_bwd(const float* const* tables, const int64_t* rows, int n_fie
                       int64_t dense_sb, const void* d_ids, int ids_i64, int64_t B, int64_t ids_sb,
                       int64_t ids_sf, const float* d_out, const float* d_A, const float* d_gout,
                       float* d_gsparse, float* d_gdense_rows, float* d_dz, void* stream);
+
+/* ---- K7 / core of K6: fused short-sequence attention ------------------------------------
+ * replaces: match scaled_dot_product_attention src/match/layers/modules.py:76-96 (+ the
+ *           split_heads / merge transposes :63-74,122-130) and ctr
+ *           _scaled_dot_product_attention src/ctr/layers/modules.py:222-240
+ * q (B,Lq,H*hs), k/v (B,Lk,H*hs) addressed with element strides (sample, position); head h
+ * is columns [h*hs,(h+1)*hs).  logits = q.k * scale; masked logits are REPLACED by -2^32+1
+ * (a fully masked row is uniform): d_row_mask (B,Lq) blanks whole query rows (the match-side
+ * (B,L,1) mask quirk, :90-91), d_key_mask (B,Lk) / causal are the conventional variants; any
+ * may be NULL/0.  out (B,Lq,H*hs).  d_stat_m / d_stat_il (B,H,Lq) receive the row max and
+ * 1/row-sum for the backward (both NULL for inference).  hs % 4 == 0, hs <= 128, L <= 256.
+ * _bwd recomputes P; d_delta (B,H,Lq) is scratch.                                        */
+int rtf_attn_fwd(const float* d_q, int64_t q_sb, int64_t q_sl, const float* d_k, int64_t k_sb,
+                 int64_t k_sl, const float* d_v, int64_t v_sb, int64_t v_sl,
+                 const float* d_row_mask, int64_t rm_sb, const float* d_key_mask, int64_t km_sb,
+                 int causal, int B, int H, int Lq, int Lk, int hs, float scale, float* d_out,
+                 int64_t o_sb, int64_t o_sl, float* d_stat_m, float* d_stat_il, void* stream);
+int rtf_attn_bwd(const float* d_q, int64_t q_sb, int64_t q_sl, const float* d_k, int64_t k_sb,
+                 int64_t k_sl, const float* d_v, int64_t v_sb, int64_t v_sl,
+                 const float* d_row_mask, int64_t rm_sb, const float* d_key_mask, int64_t km_sb,
+                 int causal, int B, int H, int Lq, int Lk, int hs, float scale,
+                 const float* d_out, int64_t o_sb, int64_t o_sl, const float* d_stat_m,
+                 const float* d_stat_il, const float* d_dout, int64_t do_sb, int64_t do_sl,
+                 float* d_delta, float* d_dq, int64_t dq_sb, int64_t dq_sl, float* d_dk,
+                 int64_t dk_sb, int64_t dk_sl, float* d_dv, int64_t dv_sb, int64_t dv_sl,
+                 void* stream);
+
+/* ---- K5: DIN local activation unit ----------------------------------------------------
+ * replaces: ctr.layers.modules.AttentionLayer.call  src/ctr/layers/modules.py:149-175
+ * q (B,d), k/v (B,L,d) (k may alias v), mask (B,L) float (0 = padded; NULL => every score is
+ * padded, as the source does when mask is not a tensor, :164-165), W (4d) + bias (1) = the
+ * Dense(1, activation) over concat([q,k,q-k,q*k]); act: 0 none, 1 relu, 2 sigmoid, 3 tanh.
+ * out (B,d) = softmax(mask(act(info.W+b))) @ v, no 1/sqrt(d).  d % 4 == 0.
+ * _bwd: d_gq (B,d), d_gk/d_gv (B,L,d), d_gw_rows (B,4d+1) per-sample dL/d[W|bias]
+ * (column-sum it with rtf_colsum).                                                        */
+int rtf_din_attn_fwd(const float* d_q, int64_t q_sb, const float* d_k, int64_t k_sb,
+                     const float* d_v, int64_t v_sb, const float* d_mask, int64_t m_sb,
+                     const float* d_W, const float* d_bias, int act, int64_t B, int L, int d,
+                     float* d_out, int64_t o_sb, void* stream);
+int rtf_din_attn_bwd(const float* d_q, int64_t q_sb, const float* d_k, int64_t k_sb,
+                     const float* d_v, int64_t v_sb, const float* d_mask, int64_t m_sb,
+                     const float* d_W, const float* d_bias, int act, int64_t B, int L, int d,
+                     const float* d_gout, int64_t go_sb, float* d_gq, int64_t gq_sb, float* d_gk,
+                     int64_t gk_sb, float* d_gv, int64_t gv_sb, float* d_gw_rows, void* stream);
+
+/* ---- K8: sampled softmax ----------------------------------------------------------------
+ * replaces: tf.nn.sampled_softmax_loss in SampledSoftmaxLayer.call
+ *           src/match/layers/modules.py:54-60 (semantics: SURVEY App. A13/A14)
+ * sampler: S unique log-uniform ids in [0,range_max) from a counter-based RNG (device kernel,
+ * no host sync); expected counts -expm1(num_tries*log1p(-P(c))).
+ * loss[b] = logsumexp([x.W[label]+b-log(te) | x.W[s_j]+b-log(se_j) (-FLT_MAX on hits)]) - true.
+ * _bwd: d_gx (B,D) and d_G (B,S+1) = dL/dlogits (column 0 = true class); the weight-row
+ * gradients are G^T x, scattered by K2 over ids = [labels | sampled].                      */
+int rtf_log_uniform_workspace(int S, size_t* bytes);
+int rtf_log_uniform_sample(uint64_t seed, int S, int64_t range_max, int64_t* d_sampled,
+                           int32_t* d_num_tries, void* d_ws, void* stream);
+int rtf_log_uniform_expected(const int64_t* d_ids, int64_t n, int64_t range_max,
+                             const int32_t* d_num_tries, float* d_out, void* stream);
+int rtf_sampled_softmax_workspace(int S, int D, size_t* bytes);
+int rtf_sampled_softmax_fwd(const float* d_x, int64_t x_sb, const float* d_W, const float* d_bias,
+                            const int64_t* d_labels, const int64_t* d_sampled,
+                            const float* d_true_exp, const float* d_samp_exp, int64_t B, int64_t N,
+                            int S, int D, int remove_hits, float* d_loss, float* d_lse, void* d_ws,
+                            int32_t* d_err, void* stream);
+int rtf_sampled_softmax_bwd(const float* d_x, int64_t x_sb, const float* d_W, const float* d_bias,
+                            const int64_t* d_labels, const int64_t* d_sampled,
+                            const float* d_true_exp, const float* d_samp_exp, int64_t B, int64_t N,
+                            int S, int D, int remove_hits, const float* d_lse,
+                            const float* d_gloss, float* d_gx, int64_t gx_sb, float* d_G,
+                            void* d_ws, void* stream);
 
 #ifdef __cplusplus
 }

@@ -7,9 +7,12 @@ from . import _lib
 from ._lib import RtfError, build, lib
 from .embedding import EmbeddingTables, SparseOptimizer, embed_bwd, embed_fwd
 from .interaction import dot_interact, dot_out_cols, embed_dot
+from .attention import attention
+from .fm import FM, FMModel, colsum
 from . import layers
 from .dlrm import DLRM, DLRMTrainer
+from . import models
 
 __all__ = ["RtfError", "build", "lib", "EmbeddingTables", "SparseOptimizer", "embed_fwd",
-           "embed_bwd", "dot_interact", "dot_out_cols", "embed_dot", "layers", "DLRM",
-           "DLRMTrainer"]
+           "embed_bwd", "dot_interact", "dot_out_cols", "embed_dot", "attention", "FM", "FMModel",
+           "colsum", "layers", "DLRM", "DLRMTrainer", "models"]

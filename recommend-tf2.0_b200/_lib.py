@@ -45,6 +45,8 @@ SIGNATURES = {
                       C.POINTER(C.c_int), _p, C.c_size_t, _p],
     "rtf_dot_interact_fwd": [_p, _i64, _int, _int, _p, _i64, _int, _p],
     "rtf_dot_interact_bwd": [_p, _p, _i64, _i64, _int, _int, _p, _p],
+    "rtf_dot_rows_fwd": [_p, _p, _int, _int, _i64, _p, _i64, _int, _p],
+    "rtf_dot_rows_bwd": [_p, _p, _int, _int, _i64, _p, _i64, _p, _p, _p],
     "rtf_embed_dot_fwd": [_p, _p, _int, _int, _p, _int, _i64, _i64, _i64, _p, _i64, _p, _i64,
                           _int, _p, _p],
     "rtf_embed_dot_bwd": [_p, _p, _int, _int, _p, _int, _i64, _i64, _i64, _p, _i64, _p, _i64,
@@ -59,6 +61,23 @@ SIGNATURES = {
                           _i64, _p, _p, _p, _p, _p],
     "rtf_fm_gather_bwd": [_p, _p, _int, _int, _int, _p, _int, _p, _i64, _p, _int, _i64, _i64,
                           _i64, _p, _p, _p, _p, _p, _p, _p],
+    "rtf_attn_fwd": [_p, _i64, _i64, _p, _i64, _i64, _p, _i64, _i64, _p, _i64, _p, _i64, _int,
+                     _int, _int, _int, _int, _int, C.c_float, _p, _i64, _i64, _p, _p, _p],
+    "rtf_attn_bwd": [_p, _i64, _i64, _p, _i64, _i64, _p, _i64, _i64, _p, _i64, _p, _i64, _int,
+                     _int, _int, _int, _int, _int, C.c_float, _p, _i64, _i64, _p, _p, _p, _i64,
+                     _i64, _p, _p, _i64, _i64, _p, _i64, _i64, _p, _i64, _i64, _p],
+    "rtf_din_attn_fwd": [_p, _i64, _p, _i64, _p, _i64, _p, _i64, _p, _p, _int, _i64, _int, _int,
+                         _p, _i64, _p],
+    "rtf_din_attn_bwd": [_p, _i64, _p, _i64, _p, _i64, _p, _i64, _p, _p, _int, _i64, _int, _int,
+                         _p, _i64, _p, _i64, _p, _i64, _p, _i64, _p, _p],
+    "rtf_log_uniform_workspace": [_int, C.POINTER(C.c_size_t)],
+    "rtf_log_uniform_sample": [C.c_uint64, _int, _i64, _p, _p, _p, _p],
+    "rtf_log_uniform_expected": [_p, _i64, _i64, _p, _p, _p],
+    "rtf_sampled_softmax_workspace": [_int, _int, C.POINTER(C.c_size_t)],
+    "rtf_sampled_softmax_fwd": [_p, _i64, _p, _p, _p, _p, _p, _p, _i64, _i64, _int, _int, _int,
+                                _p, _p, _p, _p, _p],
+    "rtf_sampled_softmax_bwd": [_p, _i64, _p, _p, _p, _p, _p, _p, _i64, _i64, _int, _int, _int,
+                                _p, _p, _p, _i64, _p, _p, _p],
 }
 
 _lib = None

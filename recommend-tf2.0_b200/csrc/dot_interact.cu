@@ -22,20 +22,17 @@ struct DotParams {
   long long rows[RTF_MAX_FIELDS];
   const void* ids;
   long long ids_sb, ids_sf;
-  const float* dense;  // gather mode: row 0 (B, D)
-  long long dense_sb;
-  const float* x;  // stacked mode: (B, F1, D); null in gather mode
+  int gather;  // 1: rows 1.. come from table[i-1][ids]; 0: every row i is rbase[i] + b*rstride[i]
+  const float* rbase[RTF_MAX_FIELDS];  // row sources (row 0 always; all rows when !gather)
+  long long rstride[RTF_MAX_FIELDS];
+  float* gbase[RTF_MAX_FIELDS];  // bwd: where dX row i of sample b goes: gbase[i] + b*gstride[i]
+  long long gstride[RTF_MAX_FIELDS];
   long long B;
   int F1, D, out_cols;
   float* out;  // fwd (B, out_cols...)
   long long out_sb;
   const float* gout;  // bwd
   long long gout_sb;
-  float* gx;      // stacked mode (B, F1, D)
-  float* gdense;  // gather mode (B, D)
-  long long gdense_sb;
-  float* gemb;  // gather mode (B, F*D)
-  long long gemb_sb;
   int32_t* err;
 };
 
@@ -43,8 +40,7 @@ __host__ __device__ inline int dot_row_stride(int D) { return D + ((D % 8 == 0) 
 
 template <typename IdT>
 __device__ __forceinline__ const float* dot_src_row(const DotParams& P, long long b, int i) {
-  if (P.x) return P.x + (b * P.F1 + i) * (long long)P.D;
-  if (i == 0) return P.dense + b * P.dense_sb;
+  if (!P.gather || i == 0) return P.rbase[i] + b * P.rstride[i];
   const long long id = load_id((const IdT*)P.ids, b * P.ids_sb + (long long)(i - 1) * P.ids_sf,
                                P.rows[i - 1], P.err);
   return id < 0 ? nullptr : P.table[i - 1] + id * P.D;
@@ -232,14 +228,7 @@ dot_bwd_kernel(const __grid_constant__ DotParams P, int warp_floats) {
           const int i = i0 + r;
           if (i < F1) {
             float4 v = acc[r];
-            float* dst;
-            if (P.gx) {
-              dst = P.gx + (b * F1 + i) * (long long)D + d0;
-            } else if (i == 0) {
-              dst = P.gdense + b * P.gdense_sb + d0;
-            } else {
-              dst = P.gemb + b * P.gemb_sb + (long long)(i - 1) * D + d0;
-            }
+            float* dst = P.gbase[i] + b * P.gstride[i] + d0;
             if (i == 0) {  // out[:, :D] is X[0] itself
               v.x += __ldg(g + d0);
               v.y += __ldg(g + d0 + 1);
@@ -311,6 +300,15 @@ static int dot_fill_tables(DotParams& P, const float* const* tables, const int64
 
 using namespace rtf;
 
+static void dot_rows_stacked(DotParams& P, const float* x, float* gx, int F1, int D) {
+  for (int i = 0; i < F1; ++i) {
+    P.rbase[i] = x + (long long)i * D;
+    P.rstride[i] = (long long)F1 * D;
+    P.gbase[i] = gx ? gx + (long long)i * D : nullptr;
+    P.gstride[i] = (long long)F1 * D;
+  }
+}
+
 extern "C" int rtf_dot_interact_fwd(const float* d_x, int64_t B, int F1, int D, float* d_out,
                                     int64_t out_sb, int out_cols, void* stream) {
   int rc = dot_check_common(B, F1, D);
@@ -321,7 +319,8 @@ extern "C" int rtf_dot_interact_fwd(const float* d_x, int64_t B, int F1, int D, 
   if (out_cols < need || out_sb < out_cols) return RTF_E_ARG;
   if ((uintptr_t)d_x % 16) return RTF_E_ALIGN;
   DotParams P = {};
-  P.x = d_x; P.B = B; P.F1 = F1; P.D = D; P.out = d_out; P.out_sb = out_sb; P.out_cols = out_cols;
+  dot_rows_stacked(P, d_x, nullptr, F1, D);
+  P.B = B; P.F1 = F1; P.D = D; P.out = d_out; P.out_sb = out_sb; P.out_cols = out_cols;
   return dot_fwd_impl(P, 0, (cudaStream_t)stream);
 }
 
@@ -334,7 +333,55 @@ extern "C" int rtf_dot_interact_bwd(const float* d_x, const float* d_gout, int64
   if (gout_sb < D + F1 * (F1 - 1) / 2) return RTF_E_ARG;
   if ((uintptr_t)d_x % 16 || (uintptr_t)d_gx % 16) return RTF_E_ALIGN;
   DotParams P = {};
-  P.x = d_x; P.B = B; P.F1 = F1; P.D = D; P.gout = d_gout; P.gout_sb = gout_sb; P.gx = d_gx;
+  dot_rows_stacked(P, d_x, d_gx, F1, D);
+  P.B = B; P.F1 = F1; P.D = D; P.gout = d_gout; P.gout_sb = gout_sb;
+  return dot_bwd_impl(P, 0, (cudaStream_t)stream);
+}
+
+// rows given one by one: row i of sample b at row_base[i] + b*row_stride[i] (HOST arrays of F1
+// device pointers / element strides).  This is how the sharded path interacts straight out of
+// the all-to-all receive buffer (source-major blocks) without a permute copy.
+extern "C" int rtf_dot_rows_fwd(const float* const* row_base, const int64_t* row_stride, int F1,
+                                int D, int64_t B, float* d_out, int64_t out_sb, int out_cols,
+                                void* stream) {
+  int rc = dot_check_common(B, F1, D);
+  if (rc) return rc;
+  if (B == 0) return 0;
+  if (!row_base || !row_stride || !d_out) return RTF_E_ARG;
+  const int need = D + F1 * (F1 - 1) / 2;
+  if (out_cols < need || out_sb < out_cols) return RTF_E_ARG;
+  DotParams P = {};
+  for (int i = 0; i < F1; ++i) {
+    if (!row_base[i]) return RTF_E_ARG;
+    if ((uintptr_t)row_base[i] % 16 || row_stride[i] % 4) return RTF_E_ALIGN;
+    P.rbase[i] = row_base[i];
+    P.rstride[i] = row_stride[i];
+  }
+  P.B = B; P.F1 = F1; P.D = D; P.out = d_out; P.out_sb = out_sb; P.out_cols = out_cols;
+  return dot_fwd_impl(P, 0, (cudaStream_t)stream);
+}
+
+extern "C" int rtf_dot_rows_bwd(const float* const* row_base, const int64_t* row_stride, int F1,
+                                int D, int64_t B, const float* d_gout, int64_t gout_sb,
+                                float* const* grad_base, const int64_t* grad_stride,
+                                void* stream) {
+  int rc = dot_check_common(B, F1, D);
+  if (rc) return rc;
+  if (B == 0) return 0;
+  if (!row_base || !row_stride || !d_gout || !grad_base || !grad_stride) return RTF_E_ARG;
+  if (gout_sb < D + F1 * (F1 - 1) / 2) return RTF_E_ARG;
+  DotParams P = {};
+  for (int i = 0; i < F1; ++i) {
+    if (!row_base[i] || !grad_base[i]) return RTF_E_ARG;
+    if ((uintptr_t)row_base[i] % 16 || row_stride[i] % 4 || (uintptr_t)grad_base[i] % 16 ||
+        grad_stride[i] % 4)
+      return RTF_E_ALIGN;
+    P.rbase[i] = row_base[i];
+    P.rstride[i] = row_stride[i];
+    P.gbase[i] = grad_base[i];
+    P.gstride[i] = grad_stride[i];
+  }
+  P.B = B; P.F1 = F1; P.D = D; P.gout = d_gout; P.gout_sb = gout_sb;
   return dot_bwd_impl(P, 0, (cudaStream_t)stream);
 }
 
@@ -355,7 +402,8 @@ extern "C" int rtf_embed_dot_fwd(const float* const* tables, const int64_t* rows
   DotParams P = {};
   rc = dot_fill_tables(P, tables, rows, n_fields);
   if (rc) return rc;
-  P.ids = d_ids; P.ids_sb = ids_sb; P.ids_sf = ids_sf; P.dense = d_dense; P.dense_sb = dense_sb;
+  P.gather = 1; P.ids = d_ids; P.ids_sb = ids_sb; P.ids_sf = ids_sf; P.rbase[0] = d_dense;
+  P.rstride[0] = dense_sb;
   P.B = B; P.F1 = F1; P.D = D; P.out = d_out; P.out_sb = out_sb; P.out_cols = out_cols;
   P.err = d_err;
   return dot_fwd_impl(P, ids_i64, (cudaStream_t)stream);
@@ -379,8 +427,13 @@ extern "C" int rtf_embed_dot_bwd(const float* const* tables, const int64_t* rows
   DotParams P = {};
   rc = dot_fill_tables(P, tables, rows, n_fields);
   if (rc) return rc;
-  P.ids = d_ids; P.ids_sb = ids_sb; P.ids_sf = ids_sf; P.dense = d_dense; P.dense_sb = dense_sb;
-  P.B = B; P.F1 = F1; P.D = D; P.gout = d_gout; P.gout_sb = gout_sb; P.gdense = d_gdense;
-  P.gdense_sb = gdense_sb; P.gemb = d_gemb; P.gemb_sb = gemb_sb;
+  P.gather = 1; P.ids = d_ids; P.ids_sb = ids_sb; P.ids_sf = ids_sf; P.rbase[0] = d_dense;
+  P.rstride[0] = dense_sb;
+  P.gbase[0] = d_gdense; P.gstride[0] = gdense_sb;
+  for (int f = 0; f < n_fields; ++f) {
+    P.gbase[1 + f] = d_gemb + (long long)f * D;
+    P.gstride[1 + f] = gemb_sb;
+  }
+  P.B = B; P.F1 = F1; P.D = D; P.gout = d_gout; P.gout_sb = gout_sb;
   return dot_bwd_impl(P, ids_i64, (cudaStream_t)stream);
 }

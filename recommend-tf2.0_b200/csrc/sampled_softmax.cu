@@ -1,0 +1,279 @@
+// K8 — sampled softmax: tf.nn.sampled_softmax_loss as SampledSoftmaxLayer.call uses it
+// (src/match/layers/modules.py:54-60; semantics restated in SURVEY.md App. A13/A14).
+//
+//   sampled, true_exp, samp_exp = log_uniform_candidate_sampler(unique=True)  — ONE draw per batch
+//   true_logit[b]  = x_b . W[label_b] + bias[label_b]              - log(true_exp[b])
+//   samp_logit[b,j]= x_b . W[s_j]     + bias[s_j]  (+ -FLT_MAX if s_j == label_b) - log(samp_exp[j])
+//   loss[b] = logsumexp([true | sampled]) - true_logit[b]          (soft label 1 on column 0)
+//
+// TF runs the sampler and the accidental-hit search as CPU ops (a host sync per step); here
+// the sampler is a device kernel (counter-based RNG, rejection to S unique ids) and the hit
+// mask is a compare inside the logits loop.  The S sampled rows are gathered once into a
+// compact (S, D) buffer that every sample's warp then streams from L2; a warp keeps x_b in
+// registers (lanes over D), reduces each logit with shuffles and folds it into a running
+// log-sum-exp.  TF's Philox stream cannot be reproduced: parity is on injected samples.
+#include <float.h>
+
+#include "rtf_common.cuh"
+
+namespace rtf {
+
+__device__ __forceinline__ uint64_t splitmix64(uint64_t x) {
+  x += 0x9E3779B97F4A7C15ull;
+  x = (x ^ (x >> 30)) * 0xBF58476D1CE4E5B9ull;
+  x = (x ^ (x >> 27)) * 0x94D049BB133111EBull;
+  return x ^ (x >> 31);
+}
+
+// P(c) = log((c+2)/(c+1)) / log(range_max+1); draw = floor(exp(u * log(range_max+1))) - 1
+__global__ void __launch_bounds__(32)
+log_uniform_sample_kernel(uint64_t seed, int S, long long range_max, long long* __restrict__ out,
+                          int32_t* __restrict__ num_tries, long long* __restrict__ table, int cap) {
+  // single warp; `table` is an open-addressing hash set of capacity `cap` (power of two, >= 2S)
+  const int lane = threadIdx.x;
+  for (int i = lane; i < cap; i += 32) table[i] = -1;
+  __syncwarp();
+  if (lane != 0) return;
+  const double log_range = log((double)range_max + 1.0);
+  int got = 0, tries = 0;
+  while (got < S) {
+    const uint64_t r = splitmix64(seed ^ splitmix64((uint64_t)tries));
+    ++tries;
+    const double u = (double)(r >> 11) * (1.0 / 9007199254740992.0);  // [0,1)
+    long long c = (long long)(exp(u * log_range)) - 1;
+    if (c < 0) c = 0;
+    if (c >= range_max) c = range_max - 1;
+    uint32_t hsh = (uint32_t)(splitmix64((uint64_t)c) & (uint64_t)(cap - 1));
+    bool dup = false;
+    while (table[hsh] != -1) {
+      if (table[hsh] == c) { dup = true; break; }
+      hsh = (hsh + 1) & (uint32_t)(cap - 1);
+    }
+    if (dup) continue;
+    table[hsh] = c;
+    out[got++] = c;
+  }
+  *num_tries = tries;
+}
+
+// expected_count(c) = -expm1(num_tries * log1p(-P(c)))  (unique=True), App. A14
+__global__ void __launch_bounds__(256)
+log_uniform_expected_kernel(const long long* __restrict__ ids, long long n, long long range_max,
+                            const int32_t* __restrict__ num_tries, float* __restrict__ out) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const double c = (double)ids[i];
+  const double p = (log(c + 2.0) - log(c + 1.0)) / log((double)range_max + 1.0);
+  out[i] = (float)(-expm1((double)*num_tries * log1p(-p)));
+}
+
+struct SsmParams {
+  const float* x; long long x_sb;   // (B, D)
+  const float* W;                   // (N, D)
+  const float* bias;                // (N) or null
+  const long long* labels;          // (B)
+  const long long* sampled;         // (S)
+  const float* true_exp;            // (B)
+  const float* samp_exp;            // (S)
+  long long B, N;
+  int S, D, remove_hits;
+  float* Ws;                        // workspace (S, D): gathered sampled rows
+  float* cs;                        // workspace (S): bias[s_j] - log(samp_exp[j])
+  float* loss; float* lse;          // (B)
+  const float* gloss;               // (B) backward
+  float* gx; long long gx_sb;       // (B, D)
+  float* G;                         // (B, S+1): dL/dlogit, column 0 = true class
+  int32_t* err;
+};
+
+__global__ void __launch_bounds__(256) ssm_gather(const __grid_constant__ SsmParams P) {
+  const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+  if (warp >= P.S) return;
+  long long id = P.sampled[warp];
+  const bool ok = id >= 0 && id < P.N;
+  if (!ok && lane == 0 && P.err) atomicOr(P.err, 1);
+  for (int c = lane; c < P.D; c += 32) P.Ws[(long long)warp * P.D + c] = ok ? P.W[id * P.D + c] : 0.f;
+  if (lane == 0) P.cs[warp] = ((ok && P.bias) ? P.bias[id] : 0.f) - logf(P.samp_exp[warp]);
+}
+
+// one warp per sample; lanes over D (CPL columns per lane)
+template <int CPL, bool BWD>
+__global__ void __launch_bounds__(256) ssm_kernel(const __grid_constant__ SsmParams P) {
+  const int lane = threadIdx.x & 31;
+  const long long b = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  if (b >= P.B) return;
+  const int D = P.D, S = P.S;
+  float xr[CPL];
+#pragma unroll
+  for (int t = 0; t < CPL; ++t) {
+    const int c = lane + 32 * t;
+    xr[t] = c < D ? P.x[b * P.x_sb + c] : 0.f;
+  }
+  const long long label = P.labels[b];
+  const bool lab_ok = label >= 0 && label < P.N;
+  if (!lab_ok && lane == 0 && P.err) atomicOr(P.err, 1);
+  float t0 = 0.f;
+#pragma unroll
+  for (int t = 0; t < CPL; ++t) {
+    const int c = lane + 32 * t;
+    if (c < D && lab_ok) t0 = fmaf(xr[t], __ldg(P.W + label * D + c), t0);
+  }
+  t0 = warp_sum(t0) + ((lab_ok && P.bias) ? P.bias[label] : 0.f) - logf(P.true_exp[b]);
+  if (!BWD) {
+    float m = t0, l = 1.f;
+    for (int j = 0; j < S; ++j) {
+      float s = 0.f;
+#pragma unroll
+      for (int t = 0; t < CPL; ++t) {
+        const int c = lane + 32 * t;
+        if (c < D) s = fmaf(xr[t], P.Ws[(long long)j * D + c], s);
+      }
+      s = warp_sum(s);
+      if (P.remove_hits && P.sampled[j] == label) s += -FLT_MAX;
+      s += P.cs[j];
+      const float mn = fmaxf(m, s);
+      l = l * expf(m - mn) + expf(s - mn);
+      m = mn;
+    }
+    if (lane == 0) {
+      const float lse = m + logf(l);
+      P.lse[b] = lse;
+      P.loss[b] = lse - t0;
+    }
+  } else {
+    const float lse = P.lse[b], g = P.gloss[b];
+    float gxr[CPL];
+    const float g0 = g * (expf(t0 - lse) - 1.f);
+#pragma unroll
+    for (int t = 0; t < CPL; ++t) {
+      const int c = lane + 32 * t;
+      gxr[t] = (c < D && lab_ok) ? g0 * __ldg(P.W + label * D + c) : 0.f;
+    }
+    float* Gb = P.G + b * (long long)(S + 1);
+    if (lane == 0) Gb[0] = g0;
+    for (int j = 0; j < S; ++j) {
+      float s = 0.f;
+      float wv[CPL];
+#pragma unroll
+      for (int t = 0; t < CPL; ++t) {
+        const int c = lane + 32 * t;
+        wv[t] = c < D ? P.Ws[(long long)j * D + c] : 0.f;
+        s = fmaf(xr[t], wv[t], s);
+      }
+      s = warp_sum(s);
+      if (P.remove_hits && P.sampled[j] == label) s += -FLT_MAX;
+      s += P.cs[j];
+      const float gj = g * expf(s - lse);
+      if (lane == 0) Gb[1 + j] = gj;
+#pragma unroll
+      for (int t = 0; t < CPL; ++t) gxr[t] = fmaf(gj, wv[t], gxr[t]);
+    }
+#pragma unroll
+    for (int t = 0; t < CPL; ++t) {
+      const int c = lane + 32 * t;
+      if (c < D) P.gx[b * P.gx_sb + c] = gxr[t];
+    }
+  }
+}
+
+template <bool BWD>
+static int ssm_launch(const SsmParams& P, cudaStream_t st) {
+  const unsigned blocks = (unsigned)((P.B * 32 + 255) / 256);
+  const int cpl = (P.D + 31) / 32;
+  if (cpl <= 1) ssm_kernel<1, BWD><<<blocks, 256, 0, st>>>(P);
+  else if (cpl <= 2) ssm_kernel<2, BWD><<<blocks, 256, 0, st>>>(P);
+  else if (cpl <= 4) ssm_kernel<4, BWD><<<blocks, 256, 0, st>>>(P);
+  else if (cpl <= 8) ssm_kernel<8, BWD><<<blocks, 256, 0, st>>>(P);
+  else return RTF_E_RANGE;
+  RTF_CHECK_LAUNCH();
+  return 0;
+}
+
+}  // namespace rtf
+
+using namespace rtf;
+
+extern "C" int rtf_log_uniform_workspace(int S, size_t* bytes) {
+  if (!bytes || S <= 0) return RTF_E_ARG;
+  size_t cap = 64;
+  while (cap < (size_t)2 * S) cap <<= 1;
+  *bytes = cap * 8;
+  return 0;
+}
+
+extern "C" int rtf_log_uniform_sample(uint64_t seed, int S, int64_t range_max, int64_t* d_sampled,
+                                      int32_t* d_num_tries, void* d_ws, void* stream) {
+  if (S <= 0 || range_max <= 0 || !d_sampled || !d_num_tries || !d_ws) return RTF_E_ARG;
+  if ((int64_t)S > range_max) return RTF_E_RANGE;  // TF would never terminate (A14)
+  int cap = 64;
+  while (cap < 2 * S) cap <<= 1;
+  log_uniform_sample_kernel<<<1, 32, 0, (cudaStream_t)stream>>>(
+      seed, S, range_max, (long long*)d_sampled, d_num_tries, (long long*)d_ws, cap);
+  RTF_CHECK_LAUNCH();
+  return 0;
+}
+
+extern "C" int rtf_log_uniform_expected(const int64_t* d_ids, int64_t n, int64_t range_max,
+                                        const int32_t* d_num_tries, float* d_out, void* stream) {
+  if (n < 0 || range_max <= 0) return RTF_E_ARG;
+  if (n == 0) return 0;
+  if (!d_ids || !d_num_tries || !d_out) return RTF_E_ARG;
+  log_uniform_expected_kernel<<<(unsigned)((n + 255) / 256), 256, 0, (cudaStream_t)stream>>>(
+      (const long long*)d_ids, n, range_max, d_num_tries, d_out);
+  RTF_CHECK_LAUNCH();
+  return 0;
+}
+
+static int ssm_fill(SsmParams& P, const float* x, int64_t x_sb, const float* W, const float* bias,
+                    const int64_t* labels, const int64_t* sampled, const float* te, const float* se,
+                    int64_t B, int64_t N, int S, int D, int remove_hits, float* ws) {
+  if (B < 0 || N <= 0 || S <= 0 || D <= 0) return RTF_E_ARG;
+  if (D > 256) return RTF_E_RANGE;
+  if (B == 0) return 0;
+  if (!x || !W || !labels || !sampled || !te || !se || !ws) return RTF_E_ARG;
+  P.x = x; P.x_sb = x_sb; P.W = W; P.bias = bias; P.labels = (const long long*)labels;
+  P.sampled = (const long long*)sampled; P.true_exp = te; P.samp_exp = se; P.B = B; P.N = N;
+  P.S = S; P.D = D; P.remove_hits = remove_hits; P.Ws = ws; P.cs = ws + (size_t)S * D;
+  return 0;
+}
+
+extern "C" int rtf_sampled_softmax_workspace(int S, int D, size_t* bytes) {
+  if (!bytes || S <= 0 || D <= 0) return RTF_E_ARG;
+  *bytes = ((size_t)S * D + S) * 4;
+  return 0;
+}
+
+extern "C" int rtf_sampled_softmax_fwd(const float* d_x, int64_t x_sb, const float* d_W,
+                                       const float* d_bias, const int64_t* d_labels,
+                                       const int64_t* d_sampled, const float* d_true_exp,
+                                       const float* d_samp_exp, int64_t B, int64_t N, int S, int D,
+                                       int remove_hits, float* d_loss, float* d_lse, void* d_ws,
+                                       int32_t* d_err, void* stream) {
+  SsmParams P = {};
+  int rc = ssm_fill(P, d_x, x_sb, d_W, d_bias, d_labels, d_sampled, d_true_exp, d_samp_exp, B, N, S,
+                    D, remove_hits, (float*)d_ws);
+  if (rc || B == 0) return rc;
+  if (!d_loss || !d_lse) return RTF_E_ARG;
+  P.loss = d_loss; P.lse = d_lse; P.err = d_err;
+  cudaStream_t st = (cudaStream_t)stream;
+  ssm_gather<<<(unsigned)((S * 32 + 255) / 256), 256, 0, st>>>(P);
+  return ssm_launch<false>(P, st);
+}
+
+extern "C" int rtf_sampled_softmax_bwd(const float* d_x, int64_t x_sb, const float* d_W,
+                                       const float* d_bias, const int64_t* d_labels,
+                                       const int64_t* d_sampled, const float* d_true_exp,
+                                       const float* d_samp_exp, int64_t B, int64_t N, int S, int D,
+                                       int remove_hits, const float* d_lse, const float* d_gloss,
+                                       float* d_gx, int64_t gx_sb, float* d_G, void* d_ws,
+                                       void* stream) {
+  SsmParams P = {};
+  int rc = ssm_fill(P, d_x, x_sb, d_W, d_bias, d_labels, d_sampled, d_true_exp, d_samp_exp, B, N, S,
+                    D, remove_hits, (float*)d_ws);
+  if (rc || B == 0) return rc;
+  if (!d_lse || !d_gloss || !d_gx || !d_G) return RTF_E_ARG;
+  P.lse = const_cast<float*>(d_lse); P.gloss = d_gloss; P.gx = d_gx; P.gx_sb = gx_sb; P.G = d_G;
+  cudaStream_t st = (cudaStream_t)stream;
+  ssm_gather<<<(unsigned)((S * 32 + 255) / 256), 256, 0, st>>>(P);
+  return ssm_launch<true>(P, st);
+}

@@ -14,7 +14,7 @@ import torch
 
 from .embedding import EmbeddingTables, SparseOptimizer
 from .interaction import dot_out_cols, embed_dot
-from .layers.core import DNN, Dense, Layer, binary_crossentropy
+from .core import DNN, Dense, Layer, binary_crossentropy
 
 
 class DLRM(Layer):

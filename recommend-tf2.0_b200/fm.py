@@ -9,7 +9,7 @@ import torch
 
 from . import _lib as L
 from .embedding import EmbeddingTables, SparseOptimizer, _ptr_array
-from .layers.core import Layer, l2
+from .core import Layer, l2
 
 
 def colsum(x: torch.Tensor, rowscale: Optional[torch.Tensor] = None) -> torch.Tensor:

@@ -1,202 +1,4 @@
-"""Keras-protocol glue the reference's model files rely on: `Layer` (build-on-first-call),
-`Dense`, `DNN`, `BatchNormalization`, `Dropout`, activations.
-
-These are the dense MLP pieces either side of the hot path: they stay on the
-framework's GEMM (torch -> cuBLAS, fp32, TF32 off) and exist so that model code written
-against the reference's layer API runs unchanged.  Initialisers follow Keras (App. A4):
-glorot_uniform kernels, zero biases.
-"""
-from __future__ import annotations
-
-import math
-from typing import Callable, Optional, Sequence
-
-import torch
-import torch.nn.functional as F
-
-
-class Layer(torch.nn.Module):
-    """Keras-style layer: `build(input_shape)` runs once on the first call, then `call`."""
-
-    def __init__(self, name: Optional[str] = None, **kwargs):
-        super().__init__()
-        self._built = False
-        self._name = name
-
-    def build(self, input_shape):  # noqa: D401
-        pass
-
-    def call(self, inputs, **kwargs):
-        raise NotImplementedError
-
-    def forward(self, inputs, *args, **kwargs):
-        if not self._built:
-            self.build(_shape_of(inputs))
-            self._built = True
-        return self.call(inputs, *args, **kwargs)
-
-    def add_weight(self, name: str, shape, initializer="glorot_uniform", regularizer=None,
-                   trainable: bool = True, dtype=torch.float32, device=None):
-        w = torch.empty(tuple(shape), dtype=dtype, device=device or _default_device())
-        _init_(w, initializer)
-        p = torch.nn.Parameter(w, requires_grad=trainable)
-        self.register_parameter(name, p)
-        if regularizer is not None:
-            self.__dict__.setdefault("_regularized", []).append((p, regularizer))
-        return p
-
-    def regularization_loss(self):
-        """Sum of the l2(λ)·Σw² terms of this layer and its children (Keras adds them to the loss)."""
-        total = 0.0
-        for m in self.modules():
-            for p, reg in m.__dict__.get("_regularized", []):
-                total = total + reg(p)
-        return total
-
-
-def _default_device():
-    return torch.device("cuda") if torch.cuda.is_available() else torch.device("cpu")
-
-
-def _shape_of(x):
-    if isinstance(x, (list, tuple)):
-        return [_shape_of(t) for t in x]
-    if isinstance(x, dict):
-        return {k: _shape_of(v) for k, v in x.items()}
-    return tuple(x.shape) if hasattr(x, "shape") else None
-
-
-def _init_(w: torch.Tensor, initializer) -> None:
-    if callable(initializer):
-        initializer(w)
-    elif initializer in ("glorot_uniform", None):
-        if w.dim() >= 2:
-            fan_in, fan_out = w.shape[0], w.shape[1]
-        else:                         # Keras: scalar / 1-D -> fans (1,1) / (n,n)
-            fan_in = fan_out = max(1, w.numel())
-        lim = math.sqrt(6.0 / (fan_in + fan_out))
-        with torch.no_grad():
-            w.uniform_(-lim, lim)
-    elif initializer == "random_normal":
-        with torch.no_grad():
-            w.normal_(0.0, 0.05)
-    elif initializer == "random_uniform":
-        with torch.no_grad():
-            w.uniform_(-0.05, 0.05)
-    elif initializer == "zeros":
-        with torch.no_grad():
-            w.zero_()
-    elif initializer == "ones":
-        with torch.no_grad():
-            w.fill_(1.0)
-    else:
-        raise ValueError(f"unknown initializer {initializer!r}")
-
-
-class l2:
-    """tensorflow.keras.regularizers.l2: λ·Σ w² (no ½), App. A3."""
-
-    def __init__(self, l2: float = 0.01):
-        self.l2 = float(l2)
-
-    def __call__(self, w):
-        return self.l2 * (w * w).sum()
-
-
-def get_activation(act) -> Optional[Callable]:
-    if act is None or act == "linear":
-        return None
-    if callable(act):
-        return act
-    table = {"relu": F.relu, "sigmoid": torch.sigmoid, "tanh": torch.tanh, "softmax":
-             lambda x: torch.softmax(x, -1)}
-    if act not in table:
-        # the reference's default att_activation='prelu' is not a Keras activation string either
-        raise ValueError(f"Unknown activation function: {act}")
-    return table[act]
-
-
-class Dense(Layer):
-    """tensorflow.keras.layers.Dense: y = act(x·W + b); contracts the last axis (A4)."""
-
-    def __init__(self, units: int, activation=None, use_bias: bool = True,
-                 kernel_regularizer=None, **kwargs):
-        super().__init__(**kwargs)
-        self.units, self.use_bias, self.kernel_regularizer = units, use_bias, kernel_regularizer
-        self.activation = get_activation(activation)
-        if isinstance(activation, torch.nn.Module):
-            self.activation_module = activation
-
-    def build(self, input_shape):
-        self.kernel = self.add_weight("kernel", (input_shape[-1], self.units), "glorot_uniform",
-                                      self.kernel_regularizer)
-        self.bias = self.add_weight("bias", (self.units,), "zeros") if self.use_bias else None
-
-    def call(self, x, **kwargs):
-        y = torch.matmul(x, self.kernel)
-        if self.bias is not None:
-            y = y + self.bias
-        return self.activation(y) if self.activation is not None else y
-
-
-class BatchNormalization(Layer):
-    """Keras defaults (A9): momentum 0.99, eps 1e-3, batch statistics in training."""
-
-    def __init__(self, center: bool = True, scale: bool = True, momentum: float = 0.99,
-                 epsilon: float = 1e-3, trainable: bool = True, **kwargs):
-        super().__init__(**kwargs)
-        self.center, self.scale, self.momentum, self.epsilon = center, scale, momentum, epsilon
-
-    def build(self, input_shape):
-        c = input_shape[-1]
-        self.gamma = self.add_weight("gamma", (c,), "ones") if self.scale else None
-        self.beta = self.add_weight("beta", (c,), "zeros") if self.center else None
-        dev = _default_device()
-        self.register_buffer("moving_mean", torch.zeros(c, device=dev))
-        self.register_buffer("moving_variance", torch.ones(c, device=dev))
-
-    def call(self, x, **kwargs):
-        shp = x.shape
-        x2 = x.reshape(-1, shp[-1])
-        y = F.batch_norm(x2, self.moving_mean, self.moving_variance, self.gamma, self.beta,
-                         self.training, 1.0 - self.momentum, self.epsilon)
-        return y.reshape(shp)
-
-
-class Dropout(Layer):
-    def __init__(self, rate: float = 0.0, **kwargs):
-        super().__init__(**kwargs)
-        self.rate = rate
-
-    def call(self, x, **kwargs):
-        return F.dropout(x, self.rate, self.training) if self.rate > 0 else x
-
-
-class DNN(Layer):
-    """ctr.layers.modules.DNN (src/ctr/layers/modules.py:114-135): a BatchNormalization created
-    inside `call` (once, A5), the Dense stack, then dropout.  `input_bn=False` gives the
-    match-side DNN (src/match/layers/modules.py:8-26), which has no BatchNormalization."""
-
-    def __init__(self, hidden_units: Sequence[int], activation="relu", dnn_dropout: float = 0.0,
-                 input_bn: bool = True, **kwargs):
-        super().__init__(**kwargs)
-        self.dnn_network = torch.nn.ModuleList([Dense(u, activation=activation) for u in hidden_units])
-        self.dropout = Dropout(dnn_dropout)
-        self.bn = BatchNormalization() if input_bn else None
-
-    def call(self, inputs, **kwargs):
-        x = inputs
-        if self.bn is not None:
-            x = self.bn(x)
-        for dnn in self.dnn_network:
-            x = dnn(x)
-        return self.dropout(x)
-
-
-def binary_crossentropy(y_true: torch.Tensor, y_pred: torch.Tensor) -> torch.Tensor:
-    """Keras `binary_crossentropy` on probabilities (A11): clip to [1e-7, 1-1e-7], then
-    -mean(y·log(p+1e-7) + (1-y)·log(1-p+1e-7))."""
-    eps = 1e-7
-    p = torch.clamp(y_pred, eps, 1.0 - eps)
-    y = y_true.to(p.dtype).reshape(p.shape)
-    return -(y * torch.log(p + eps) + (1.0 - y) * torch.log(1.0 - p + eps)).mean()
+"""Keras-protocol glue (Layer, Dense, DNN, ...) — defined in ../core.py, re-exported here so
+that `layers.core` keeps working as an import path."""
+from ..core import (BatchNormalization, DNN, Dense, Dropout, Layer, binary_crossentropy,  # noqa: F401
+                    get_activation, l2, _default_device, _init_, _shape_of)

@@ -1,0 +1,192 @@
+"""The callers either side of the hot path: the reference's model classes (L3) rebuilt on the
+drop-in layers, with the reference's constructor signatures.  Where the reference's `call` is
+broken the layer code is followed and the glue is defined here; every such
+place is marked.  Dense MLP pieces are framework GEMMs (core.py)."""
+from __future__ import annotations
+
+from typing import Optional
+
+import torch
+
+from .embedding import EmbeddingTables, SparseOptimizer
+from .layers.core import DNN, BatchNormalization, Dense, Dropout, Layer
+from .layers.ctr import FM, AttentionLayer
+from .layers.ctr import MultiHeadAttention as CtrMultiHeadAttention
+from .layers.embedding import _as_int_ids
+from .layers.match import DNN as MatchDNN
+from .layers.match import SampledSoftmaxLayer, TransformerEncoder
+
+
+class DeepFM(Layer):
+    """src/ctr/deep_fm/model.py:17-65.  Embeddings use 'random_normal' (:35); the FM layer gets
+    first_inputs = concat(dense, sparse_embed) and the 2-D sparse_embed as second_inputs
+    (:56-59), exactly as the source does."""
+
+    def __init__(self, feature_columns, hidden_units=(128, 64, 32), dnn_dropout=0.0,
+                 activation="relu", fm_w_reg=1e-6, embed_reg=1e-6,
+                 sparse_optimizer: Optional[SparseOptimizer] = None, seed=None):
+        super().__init__()
+        self.dense_feature_columns, self.sparse_feature_columns = feature_columns
+        rows = [f["feat_num"] for f in self.sparse_feature_columns]
+        dims = [f["embed_dim"] for f in self.sparse_feature_columns]
+        self.embed_layers = EmbeddingTables(rows, dims, "random_normal", optimizer=sparse_optimizer,
+                                            seed=seed)
+        self.feature_length = len(self.dense_feature_columns) + sum(dims)
+        self.fm = FM(self.feature_length, fm_w_reg)
+        self.dnn = DNN(hidden_units, activation, dnn_dropout)
+        self.dense = Dense(1, activation=None)
+
+    def call(self, inputs, **kwargs):
+        dense_inputs, sparse_inputs = inputs
+        sparse_embed = self.embed_layers.lookup(_as_int_ids(sparse_inputs))      # (B, F*D)
+        embeds = torch.cat([dense_inputs, sparse_embed], dim=-1)
+        fm_outputs = self.fm([embeds, sparse_embed])                              # (B, 1)
+        deep_outputs = self.dense(self.dnn(embeds))                               # (B, 1)
+        return torch.sigmoid(fm_outputs + deep_outputs)
+
+
+class AutoInt(Layer):
+    """AutoInt on (B, F, d) field embeddings: `n_layers` stacked interacting layers
+    (ctr MultiHeadAttention, use_res=True), flatten, Dense(1), sigmoid.
+
+    The reference's AutoInt (src/ctr/autoint/model.py:44-55) feeds a 2-D (B, 26*D+13) tensor
+    into the attention layer (batch-folding bug) with one layer / one head; BASELINE's config
+    (3 layers, 2 heads, 39 fields, d=16) needs the paper's dense-field embedding x_j * v_j, which
+    is defined here: `dense_embed` holds one d-vector per dense feature."""
+
+    def __init__(self, feature_columns, head_size=16, head_num=2, n_layers=3, use_res=True,
+                 activation="relu", embed_reg=1e-4, scale="reference",
+                 sparse_optimizer: Optional[SparseOptimizer] = None, seed=None):
+        super().__init__()
+        self.dense_feature_columns, self.sparse_feature_columns = feature_columns
+        rows = [f["feat_num"] for f in self.sparse_feature_columns]
+        dims = [f["embed_dim"] for f in self.sparse_feature_columns]
+        assert len(set(dims)) == 1
+        self.d = dims[0]
+        self.embed_layers = EmbeddingTables(rows, dims, "random_uniform", optimizer=sparse_optimizer,
+                                            seed=seed)
+        nd = len(self.dense_feature_columns)
+        self.dense_embed = torch.nn.Parameter(
+            torch.empty(nd, self.d, device=self.embed_layers.weights[0].device).uniform_(-0.05, 0.05))
+        self.att_layers = torch.nn.ModuleList(
+            [CtrMultiHeadAttention(head_size, head_num, activation=activation, use_res=use_res,
+                                   scale=scale) for _ in range(n_layers)])
+        self.out_dense = Dense(1, activation=None)
+
+    def call(self, inputs, **kwargs):
+        dense_inputs, sparse_inputs = inputs
+        B, F = sparse_inputs.shape
+        sparse_embed = self.embed_layers.lookup(_as_int_ids(sparse_inputs)).reshape(B, F, self.d)
+        dense_embed = dense_inputs.unsqueeze(-1) * self.dense_embed.unsqueeze(0)   # x_j * v_j
+        x = torch.cat([dense_embed, sparse_embed], dim=1)                          # (B, 39, d)
+        for layer in self.att_layers:
+            x = layer(x)
+        return torch.sigmoid(self.out_dense(x.reshape(B, -1)))
+
+
+class DIN(Layer):
+    """DIN with the local activation unit on the classic input the reference's loader produces
+    (src/ctr/utils/data_process.py:176,215-216): hist (B, maxlen, n_behavior) ids, target item
+    (B, n_behavior) ids sharing the item tables (src/ctr/din/model.py:71-72), a (B, maxlen) mask
+    = (hist[..., 0] != 0).  The reference's DIN.call never reaches a loss (reshape bug :79-81)
+    and uses self-attention instead of AttentionLayer; this follows the layer + the paper."""
+
+    def __init__(self, behavior_feature_nums, embed_dim=8, att_activation="sigmoid",
+                 ffn_hidden_units=(80, 40), maxlen=100, dnn_dropout=0.0, embed_reg=1e-4,
+                 sparse_optimizer: Optional[SparseOptimizer] = None, seed=None):
+        super().__init__()
+        nb = len(behavior_feature_nums)
+        self.nb, self.embed_dim, self.maxlen = nb, embed_dim, maxlen
+        self.embed_layers = EmbeddingTables(list(behavior_feature_nums), [embed_dim] * nb,
+                                            "random_uniform", optimizer=sparse_optimizer, seed=seed)
+        self.attention_layer = AttentionLayer(1, activation=att_activation)
+        self.bn = BatchNormalization()
+        self.ffn = torch.nn.ModuleList([Dense(u, activation="relu") for u in ffn_hidden_units])
+        self.dropout = Dropout(dnn_dropout)
+        self.final_output = Dense(1)
+
+    def call(self, inputs, **kwargs):
+        hist, target = inputs                       # (B, L, nb) ids, (B, nb) ids
+        hist, target = _as_int_ids(hist), _as_int_ids(target)
+        tabs = tuple(range(self.nb))
+        k = self.embed_layers.lookup(hist, tabs, "BLF")            # (B, L, nb*D) — shared tables
+        q = self.embed_layers.lookup(target, tabs, "BF")           # (B, nb*D)
+        mask = (hist[..., 0] != 0).to(torch.float32)
+        user_info = self.attention_layer([q, k, k, mask])
+        x = self.bn(torch.cat([user_info, q], dim=-1))
+        for dense in self.ffn:
+            x = dense(x)
+        return torch.sigmoid(self.final_output(self.dropout(x)))
+
+
+class SASRec(Layer):
+    """src/match/sasrec/model.py:19-97: three separate tables (seq/pos/neg item, :75-79), no
+    positional embedding (:74), x *= mask before and after every block (:82,86), last position,
+    dot scores and the log loss (:88-95).  Returns (logits (B, 1+neg_len), loss)."""
+
+    def __init__(self, item_num, embed_dim=64, blocks=2, num_heads=1, ffn_hidden_unit=128,
+                 dropout=0.0, seq_len=10, neg_len=100, layer_norm_eps=1e-6,
+                 sparse_optimizer: Optional[SparseOptimizer] = None, seed=None):
+        super().__init__()
+        self.seq_len, self.neg_len, self.embed_dim = seq_len, neg_len, embed_dim
+        self.tables = EmbeddingTables([item_num] * 3, [embed_dim] * 3, "random_uniform",
+                                      optimizer=sparse_optimizer, seed=seed)
+        self.encoder_layer = torch.nn.ModuleList(
+            [TransformerEncoder(embed_dim, num_heads, ffn_hidden_unit, dropout, layer_norm_eps)
+             for _ in range(blocks)])
+
+    def call(self, inputs, **kwargs):
+        seq, pos, neg = (_as_int_ids(t) for t in inputs)     # (B,L), (B,1), (B,neg_len)
+        mask = (seq != 0).to(torch.float32).unsqueeze(-1)                       # :72
+        seq_embed = self.tables.lookup(seq, (0,), "BL")                         # (B,L,D)
+        pos_embed = self.tables.lookup(pos, (1,), "BL")
+        neg_embed = self.tables.lookup(neg, (2,), "BL")
+        att_outputs = seq_embed * mask                                          # :81-82
+        for block in self.encoder_layer:
+            att_outputs = block([att_outputs, mask])
+            att_outputs = att_outputs * mask                                    # :86
+        seq_info = att_outputs[:, -1:, :]                                       # :88
+        pos_scores = (seq_info * pos_embed).sum(-1)
+        neg_scores = (seq_info * neg_embed).sum(-1)
+        loss = (-torch.log(torch.sigmoid(pos_scores)) -
+                torch.log(1 - torch.sigmoid(neg_scores))).mean() / 2           # :93-95
+        return torch.cat([pos_scores, neg_scores], dim=-1), loss
+
+
+class YoutubeDNN(Layer):
+    """Two towers + sampled softmax.  conventional=True (BASELINE config): the class weights are
+    an item table (item_num, D) and num_classes = item_num.  conventional=False reproduces
+    src/match/youtube_dnn/model.py:43-61 literally (weights = in-batch item tower output,
+    num_classes = tower width)."""
+
+    def __init__(self, user_feature_nums, item_num, embed_dim=64, user_dnn_hidden_units=(64, 32),
+                 num_sampled=5, conventional=True, sparse_optimizer: Optional[SparseOptimizer] = None,
+                 seed=None):
+        super().__init__()
+        self.conventional, self.num_sampled, self.item_num = conventional, num_sampled, item_num
+        nu = len(user_feature_nums)
+        self.user_tables = EmbeddingTables(list(user_feature_nums), [embed_dim] * nu,
+                                           optimizer=sparse_optimizer, seed=seed)
+        width = user_dnn_hidden_units[-1]
+        self.item_table = EmbeddingTables([item_num], [width if conventional else embed_dim],
+                                          optimizer=None, seed=seed)
+        self.user_dnn = MatchDNN(user_dnn_hidden_units)
+        self.item_dnn = None if conventional else MatchDNN(user_dnn_hidden_units)
+        self.sampler_layer = SampledSoftmaxLayer(num_sampled)
+        self._step = 0
+
+    def call(self, inputs, sampled_values=None, **kwargs):
+        from .layers.match import sampled_softmax_loss
+        user_ids, item_ids = (_as_int_ids(t) for t in inputs[:2])
+        user_out = self.user_dnn(self.user_tables.lookup(user_ids))             # (B, width)
+        self._step += 1
+        if self.conventional:
+            loss = sampled_softmax_loss(self.item_table.weights[0], None, item_ids, user_out,
+                                        self.num_sampled, self.item_num,
+                                        sampled_values=sampled_values, seed=self._step,
+                                        err=self.item_table.err)
+            return loss.unsqueeze(1)
+        item_out = self.item_dnn(self.item_table.lookup(item_ids.reshape(-1, 1)))
+        labels = inputs[2]
+        return self.sampler_layer([item_out.unsqueeze(1), user_out.unsqueeze(1), labels],
+                                  sampled_values=sampled_values)
