@@ -1,0 +1,258 @@
+"""C1 — multi-GPU embedding model parallelism for the DLRM path.
+
+The reference only knows tf.distribute.MirroredStrategy: every table is replicated and, being
+l2-regularised, its dense gradient is all-reduced every step (src/ctr/fm/train.py:43-50).
+Here each table lives on ONE rank (table-wise sharding, greedy balance of lookup count then
+bytes); the dense MLPs stay data-parallel.  One process per GPU, torch.distributed (NCCL over
+NVLink) for the plumbing:
+
+  forward   ids (B_local,F) --all-gather--> (B_global,F)
+            K1 on the owner: local tables x global batch          -> (B_global, T_me*D)
+            all-to-all of pooled rows (async, overlaps the bottom MLP)
+            K4 reads the receive buffer in place (rows addressed by base+stride, blocks ordered
+            by source rank) — interaction output identical to the single-GPU one
+  backward  K4 bwd writes dX rows straight into the send buffer of the reverse all-to-all
+            (async, overlaps the bottom-MLP backward) -> K2 + fused sparse Adam on the owner
+            (no table gradient ever crosses the wire as a dense tensor); MLP grads all-reduce.
+
+Row-wise sharding of the >= 5 M-row tables (north star) is the next step: at 180 GB per GPU it
+is a load-balance refinement (26 tables over 8 ranks = 4/3/3/...), not a capacity need.
+The exchange helpers are device-agnostic (gloo on CPU in tests); only lookups/interaction
+need CUDA.
+"""
+from __future__ import annotations
+
+import ctypes as C
+from typing import List, Optional, Sequence
+
+import torch
+import torch.distributed as dist
+
+from . import _lib as L
+from .core import DNN, Dense, Layer, binary_crossentropy
+from .embedding import EmbeddingTables, SparseOptimizer, embed_fwd
+from .interaction import dot_out_cols
+
+
+def plan_table_owners(rows: Sequence[int], dims: Sequence[int], world: int) -> List[int]:
+    """Greedy table-wise placement: biggest tables first, each to the rank with the fewest
+    tables (every table costs one lookup per sample), ties broken by resident bytes, then rank."""
+    order = sorted(range(len(rows)), key=lambda t: (-rows[t] * dims[t], t))
+    count, nbytes = [0] * world, [0] * world
+    owner = [0] * len(rows)
+    for t in order:
+        g = min(range(world), key=lambda r: (count[r], nbytes[r], r))
+        owner[t] = g
+        count[g] += 1
+        nbytes[g] += rows[t] * dims[t] * 4
+    return owner
+
+
+class ShardLayout:
+    """Static description of who owns what and where a table's rows sit in the exchange
+    buffers.  slots[g] = tables owned by rank g (ascending); in a receive buffer the block of
+    source g is (B_local, T_g, D) at element offset B_local*D*sum(T_<g)."""
+
+    def __init__(self, rows, dims, world, rank, owners=None):
+        self.world, self.rank = world, rank
+        self.owners = list(owners) if owners is not None else plan_table_owners(rows, dims, world)
+        self.slots = [[t for t, o in enumerate(self.owners) if o == g] for g in range(world)]
+        self.T = [len(s) for s in self.slots]
+        self.slot_of = {}
+        for g, s in enumerate(self.slots):
+            for j, t in enumerate(s):
+                self.slot_of[t] = (g, j)
+        self.n_tables = len(rows)
+
+    def fwd_splits(self, B_local: int, D: int):
+        """(input_split, output_split) element counts of the forward all-to-all on this rank."""
+        me = self.T[self.rank]
+        return [B_local * me * D] * self.world, [B_local * t * D for t in self.T]
+
+    def block_offsets(self, B_local: int, D: int):
+        off, acc = [], 0
+        for t in self.T:
+            off.append(acc)
+            acc += B_local * t * D
+        return off, acc
+
+    def row_location(self, table: int, B_local: int, D: int):
+        """(element offset, element stride between samples) of `table`'s row for local sample 0
+        inside a receive / reverse-send buffer."""
+        g, j = self.slot_of[table]
+        off, _ = self.block_offsets(B_local, D)
+        return off[g] + j * D, self.T[g] * D
+
+
+def exchange_ids(ids_local: torch.Tensor, world: int, group=None) -> torch.Tensor:
+    out = ids_local.new_empty((ids_local.shape[0] * world,) + tuple(ids_local.shape[1:]))
+    dist.all_gather_into_tensor(out, ids_local.contiguous(), group=group)
+    return out
+
+
+def exchange_rows_fwd(local_out: torch.Tensor, layout: ShardLayout, B_local: int, D: int,
+                      async_op=False, group=None):
+    """owner-major -> sample-owner: local_out (B_global, T_me*D) -> flat receive buffer of
+    source-ordered blocks.  Returns (recv, work)."""
+    ins, outs = layout.fwd_splits(B_local, D)
+    recv = local_out.new_empty(sum(outs))
+    work = dist.all_to_all_single(recv, local_out.reshape(-1), outs, ins, group=group,
+                                  async_op=async_op)
+    return recv, work
+
+
+def exchange_rows_bwd(grad_send: torch.Tensor, layout: ShardLayout, B_local: int, D: int,
+                      async_op=False, group=None):
+    """reverse of exchange_rows_fwd: flat source-ordered blocks -> (B_global, T_me*D) on owners."""
+    ins, outs = layout.fwd_splits(B_local, D)          # reversed roles
+    recv = grad_send.new_empty(sum(ins))
+    work = dist.all_to_all_single(recv, grad_send, ins, outs, group=group, async_op=async_op)
+    return recv.view(B_local * layout.world, layout.T[layout.rank] * D), work
+
+
+def _row_tables(layout: ShardLayout, recv: torch.Tensor, dense: torch.Tensor, B_local: int, D: int):
+    """HOST arrays (base pointers, strides) of the F1 rows of a sample in ORIGINAL table order:
+    row 0 = dense (bottom-MLP output), row 1+t = table t's row inside `recv`."""
+    base = [dense.data_ptr()]
+    stride = [dense.stride(0)]
+    p0 = recv.data_ptr()
+    for t in range(layout.n_tables):
+        off, st = layout.row_location(t, B_local, D)
+        base.append(p0 + off * 4)
+        stride.append(st)
+    return (C.c_void_p * len(base))(*base), (C.c_int64 * len(stride))(*stride)
+
+
+class _ShardedInteractFn(torch.autograd.Function):
+    """K4 over [dense | received rows]; backward launches the reverse all-to-all asynchronously
+    and parks the handle on the model (K2 runs in ShardedDLRM.finish_backward)."""
+
+    @staticmethod
+    def forward(ctx, model: "ShardedDLRM", dense, recv, pad_to):
+        dense = dense.contiguous()
+        lay = model.layout
+        B, D = dense.shape
+        F1 = lay.n_tables + 1
+        cols = dot_out_cols(F1, D, pad_to)
+        out = torch.empty((B, cols), dtype=torch.float32, device=dense.device)
+        rb, rs = _row_tables(lay, recv, dense, B, D)
+        L.check(L.lib().rtf_dot_rows_fwd(rb, rs, F1, D, B, out.data_ptr(), cols, cols,
+                                         L.current_stream_ptr()), "rtf_dot_rows_fwd")
+        ctx.model = model
+        ctx.save_for_backward(dense, recv)
+        return out
+
+    @staticmethod
+    def backward(ctx, gout):
+        dense, recv = ctx.saved_tensors
+        model = ctx.model
+        lay = model.layout
+        gout = gout.contiguous()
+        B, D = dense.shape
+        F1 = lay.n_tables + 1
+        gdense = torch.empty_like(dense)
+        gsend = torch.empty_like(recv)
+        rb, rs = _row_tables(lay, recv, dense, B, D)
+        gb, gs = _row_tables(lay, gsend, gdense, B, D)
+        L.check(L.lib().rtf_dot_rows_bwd(rb, rs, F1, D, B, gout.data_ptr(), gout.stride(0), gb, gs,
+                                         L.current_stream_ptr()), "rtf_dot_rows_bwd")
+        grecv, work = exchange_rows_bwd(gsend, lay, B, D, async_op=True)
+        model._pending = (grecv, work, gsend)
+        return None, gdense, None, None
+
+
+class ShardedDLRM(Layer):
+    """DLRM (same constructor as dlrm.DLRM) with table-wise sharded embeddings."""
+
+    def __init__(self, feature_columns, bot_dnn_hidden_units=(64, 32, 16),
+                 top_dnn_hidden_units=(128, 64), activation="relu", dnn_dropout=0.0, embed_reg=1e-4,
+                 sparse_optimizer: Optional[SparseOptimizer] = None, pad_to: int = 1,
+                 input_bn: bool = True, seed: Optional[int] = None, owners=None):
+        super().__init__()
+        self.world, self.rank = dist.get_world_size(), dist.get_rank()
+        self.dense_feature_columns, self.sparse_feature_columns = feature_columns
+        rows = [f["feat_num"] for f in self.sparse_feature_columns]
+        dims = [f["embed_dim"] for f in self.sparse_feature_columns]
+        if len(set(dims)) != 1 or bot_dnn_hidden_units[-1] != dims[0]:
+            raise ValueError("dot interaction needs equal embed_dim == bot_dnn_hidden_units[-1]")
+        self.D, self.pad_to, self.embed_reg = dims[0], pad_to, embed_reg
+        self.layout = ShardLayout(rows, dims, self.world, self.rank, owners)
+        mine = self.layout.slots[self.rank]
+        # per-table seeds so that a table's init does not depend on the sharding
+        self.embed_layers = EmbeddingTables([rows[t] for t in mine], [dims[t] for t in mine],
+                                            "random_uniform", optimizer=sparse_optimizer,
+                                            seed=None if seed is None else seed + 1 + self.rank)
+        if seed is not None:
+            torch.manual_seed(seed)                 # identical MLP init on every rank
+        self.bot_dnn = DNN(bot_dnn_hidden_units, activation, dnn_dropout, input_bn=input_bn)
+        self.top_dnn = DNN(top_dnn_hidden_units, activation, dnn_dropout, input_bn=input_bn)
+        self.final_dense = Dense(1, activation=None)
+        self._pending = None
+        self._saved = None
+        self.register_buffer("_mine_idx", torch.as_tensor(mine, dtype=torch.int64,
+                                                          device=self.embed_layers.err.device))
+
+    def call(self, inputs, **kwargs):
+        dense_inputs, sparse_inputs = inputs
+        lay, D = self.layout, self.D
+        B_local = sparse_inputs.shape[0]
+        ids_global = exchange_ids(sparse_inputs, self.world)                       # (B_global, F)
+        local_ids = ids_global.index_select(1, self._mine_idx).contiguous()        # (B_global, T_me)
+        with torch.no_grad():
+            local_out = embed_fwd(list(self.embed_layers.weights), local_ids, "BF", None,
+                                  err=self.embed_layers.err)
+        recv, work = exchange_rows_fwd(local_out, lay, B_local, D, async_op=True)
+        dense_fea = self.bot_dnn(dense_inputs)            # overlaps the all-to-all
+        work.wait()
+        self._saved = local_ids
+        x = _ShardedInteractFn.apply(self, dense_fea, recv, self.pad_to)
+        return torch.sigmoid(self.final_dense(self.top_dnn(x)))
+
+    def finish_backward(self):
+        """Wait for the reverse exchange and run K2 (+ fused sparse optimizer) on the owner."""
+        if self._pending is None:
+            return
+        grecv, work, _keep = self._pending
+        work.wait()
+        self.embed_layers.apply_sparse_grad(self._saved, list(range(len(self.embed_layers.weights))),
+                                            grecv)
+        self._pending = None
+
+    def dense_parameters(self):
+        emb = {id(p) for p in self.embed_layers.parameters()}
+        return [p for p in self.parameters() if id(p) not in emb]
+
+
+class ShardedDLRMTrainer:
+    """Per-rank step: local loss / world (so that summed gradients equal the global-batch mean,
+    as MirroredStrategy scales them, App. A18), reverse exchange + K2 on owners, one flat
+    all-reduce of the MLP gradients, dense Adam."""
+
+    def __init__(self, model: ShardedDLRM, lr: float = 1e-3):
+        self.model, self.lr = model, lr
+        if model.embed_layers.optimizer is None:
+            model.embed_layers.set_optimizer(SparseOptimizer("adam", lr=lr, l2=model.embed_reg))
+        self.dense_opt = None
+
+    def step(self, dense, sparse, labels) -> torch.Tensor:
+        m = self.model
+        m.embed_layers.begin_step()
+        pred = m([dense, sparse])
+        if self.dense_opt is None:
+            params = m.dense_parameters()
+            for p in params:                               # same start on every rank
+                dist.broadcast(p.data, 0)
+            self.dense_opt = torch.optim.Adam(params, lr=self.lr, eps=1e-7, fused=dense.is_cuda)
+        loss = binary_crossentropy(labels, pred)
+        self.dense_opt.zero_grad(set_to_none=True)
+        (loss / m.world).backward()
+        m.finish_backward()
+        grads = [p.grad for p in m.dense_parameters() if p.grad is not None]
+        flat = torch.cat([g.reshape(-1) for g in grads])
+        dist.all_reduce(flat)
+        off = 0
+        for g in grads:
+            g.copy_(flat[off:off + g.numel()].view_as(g))
+            off += g.numel()
+        self.dense_opt.step()
+        return loss.detach()
