@@ -333,10 +333,14 @@ def run_b200(args):
                     "algorithmic_bytes_per_launch": top[1]["algorithmic_bytes"],
                     "ms_per_launch": top[1]["ms"]}
         cpu = None
-        if not args.no_cpu_baseline:
+        if not args.no_cpu_baseline and world == 1:     # reported on rank 0 at N=1 only
             cpu = cpu_reference_run(args, steps=3, warmup=1)
             cpu = {k: cpu[k] for k in ("value", "unit", "cores", "kind", "sample")}
-        per_step = 2 + embed_bwd_launches(CRITEO_ROWS, len(CRITEO_ROWS))
+        if world == 1:   # fused gather+dot fwd, its bwd, K2 pipeline
+            per_step = 2 + embed_bwd_launches(CRITEO_ROWS, len(CRITEO_ROWS))
+        else:            # per rank: K1 + dot-rows fwd/bwd + K2 over the rank's own tables
+            mine = [CRITEO_ROWS[t] for t in model.layout.slots[0]]
+            per_step = (3 + embed_bwd_launches(mine, len(mine))) * world
         line = {"metric": "dlrm_train_samples_per_sec", "value": B * world * K / (ms_total * 1e-3),
                 "unit": "samples/s", "n_gpus": world, "steps": K, "warmup": W,
                 "ms_per_step": ms_total / K, "higher_is_better": True, "scaling": "weak",

@@ -1,0 +1,110 @@
+"""The oracle against golden vectors produced by the REFERENCE'S OWN layer source executed over
+the numpy TF stand-in (tools/make_golden.py).  float64 on both sides: agreement to ~1e-12."""
+import os
+
+import numpy as np
+import pytest
+
+from oracle import attention as OA
+from oracle import embedding as OE
+from oracle import interaction as OI
+
+GOLD = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+
+
+def G(name):
+    return dict(np.load(os.path.join(GOLD, name + ".npz")))
+
+
+def close(a, b, tol=1e-11):
+    np.testing.assert_allclose(a, b, rtol=tol, atol=tol)
+
+
+def test_golden_files_present():
+    names = sorted(f for f in os.listdir(GOLD) if f.endswith(".npz"))
+    assert len(names) >= 11
+
+
+def test_fm_layer_2d_and_3d_quirks():
+    g = G("ctr_fm_layer")
+    close(OI.fm_layer(g["first"], g["second2"], g["w"]), g["out2"])
+    out3 = OI.fm_layer(g["first"], g["second3"], g["w"])
+    assert out3.shape == g["out3"].shape == (8 * 8, 1)          # (B*D, 1): the shape bug
+    close(out3, g["out3"])
+
+
+def test_fm_model_onehot():
+    g = G("ctr_fm_model")
+    close(OI.fm_model_onehot(g["dense"], g["sparse"], list(g["feat_nums"]), g["w0"], g["w"], g["V"]), g["out"])
+
+
+def test_din_attention_layer():
+    g = G("ctr_attention_layer")
+    close(OA.din_attention_layer(g["q"], g["k"], g["v"], g["mask"], g["W"], g["b"], "sigmoid"), g["out_mask"])
+    close(OA.din_attention_layer(g["q"], g["k"], g["v"], None, g["W"], g["b"], "sigmoid"), g["out_nomask"])
+    close(g["out_nomask"], g["v"].mean(1))                       # uniform weights quirk
+    close(g["out_mask"][0], g["v"][0].mean(0))                   # fully padded sample -> uniform
+    assert int(g["prelu_accepted"]) == 0                         # 'prelu' is not an activation string
+
+
+def test_ctr_multihead_attention():
+    g = G("ctr_multihead_attention")
+    close(OA.ctr_mha(g["x"], g["x"], g["x"], g["Wq"], g["Wk"], g["Wv"], 2, 16, "relu", g["W0"]), g["out"])
+    close(OA.ctr_mha(g["x"], g["x"], g["x"], g["Wq1"], g["Wk1"], g["Wv1"], 1, 8, "relu", None), g["out1"])
+
+
+def test_ctr_sdpa_util_mask_none_is_uniform():
+    g = G("ctr_sdpa_util")
+    close(OA.match_sdpa(g["q"], g["k"], g["v"], g["mask"]), g["out_mask"])
+    close(g["out_nomask"], np.broadcast_to(g["v"].mean(-2, keepdims=True), g["v"].shape))
+
+
+def test_match_mha_and_encoder():
+    g = G("match_transformer_encoder")
+    close(OA.match_mha(g["x"], g["x"], g["x"], g["mask"], g["wq"], g["bq"], g["wk"], g["bk"], g["wv"], g["bv"], 1),
+          g["out_mha"])
+    close(OA.transformer_encoder(g["x"], g["mask"], g, 1), g["out_enc"], 1e-10)
+    p4 = {k[3:]: v for k, v in g.items() if k.startswith("h4_")}
+    close(OA.transformer_encoder(g["x4"], g["mask4"], p4, 4), g["out_enc4"], 1e-10)
+
+
+def test_pooling_layer():
+    g = G("match_pooling_layer")
+    st = np.stack([g["t0"], g["t1"], g["t2"]], -1)
+    close(st.mean(-1), g["mean"]); close(st.sum(-1), g["sum"]); close(st.max(-1), g["max"])
+    close(g["single"], g["t0"])
+
+
+def test_sampled_softmax_layer():
+    g = G("match_sampled_softmax_layer")
+    item, user = g["item"][:, 0], g["user"][:, 0]
+    want = OA.sampled_softmax_loss(item, np.zeros(32), g["labels"], user, g["sampled"], g["true_exp"], g["samp_exp"])
+    close(want[:, None], g["loss"])
+
+
+def test_sasrec_forward():
+    g = G("match_sasrec")
+    seq, pos, neg = g["seq"], g["pos"], g["neg"]
+    mask = (seq != 0).astype(np.float64)[:, :, None]
+    x = OE.embed_lookup_concat([g["seq_table"]], seq[:, None, :])[..., :].astype(np.float64)
+    x = g["seq_table"][seq] * mask
+    for bi in range(2):
+        p = {k[3:]: v for k, v in g.items() if k.startswith(f"b{bi}_")}
+        x = OA.transformer_encoder(x, mask, p, 1) * mask
+    logits, loss = OA.sasrec_scores_loss(x, g["pos_table"][pos], g["neg_table"][neg])
+    close(logits, g["logits"], 1e-9)
+    close(loss, g["loss"], 1e-9)
+
+
+def test_embedding_concat_bit_exact():
+    g = G("dlrm_embedding_concat")
+    tabs = [g[f"t{i}"] for i in range(5)]
+    out = OE.embed_lookup_concat([t.astype(np.float32) for t in tabs], g["sparse"][:, :, None])[:, 0]
+    assert np.array_equal(out, g["out"].astype(np.float32))
+
+
+def test_dice():
+    g = G("ctr_dice")
+    p = 1 / (1 + np.exp(-(g["x"] / np.sqrt(1 + 1e-3))))
+    close(g["alpha"] * (1 - p) * g["x"] + p * g["x"], g["out"])
+    assert abs(float(g["alpha"])) <= np.sqrt(3)
