@@ -42,6 +42,9 @@ def parse_args():
     ap.add_argument("--ids", default="uniform", choices=["uniform", "zipf"])
     ap.add_argument("--cpu-batch", type=int, default=2048)
     ap.add_argument("--cpu-row-cap", type=int, default=1_000_000)
+    ap.add_argument("--mlp-gemm", default="bf16x9", choices=["bf16x9", "native"],
+                    help="dense-MLP GEMMs: cuBLAS 12.9 FP32 emulation (BF16x9, fp32-accurate) or SGEMM")
+    ap.add_argument("--pad-to", type=int, default=8, help="round the interaction width up (479 -> 480)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-kernel-timing", action="store_true")
     return ap.parse_args()
@@ -245,7 +248,31 @@ def time_kernels(pkg, model, dev_batches, peaks_gbs):
     return out
 
 
+CUDA_LIB = "/usr/local/cuda/lib64"
+
+
+def preload_cublas_fp32_emulation():
+    """The dense MLPs either side of the hot path are plain library GEMMs.  The
+    image's cuBLAS 12.9 can run fp32 GEMMs as 9 BF16 tensor-core products of a 3-way split
+    (CUBLAS_COMPUTE_32F_EMULATED_16BFX9) — fp32-accurate (measured error vs fp64 below native
+    SGEMM's, tools/probe_cublas_emulation.py) at ~2.4x the SGEMM rate.  torch bundles cuBLAS
+    12.8, so the 12.9 libraries are loaded first (same SONAME => torch binds to them) and the
+    emulation is switched on through cuBLAS's own environment variable.  Must run before
+    `import torch`.  Returns a description for the JSON line."""
+    import ctypes
+    libs = [os.path.join(CUDA_LIB, n) for n in ("libcublasLt.so.12", "libcublas.so.12")]
+    if "torch" in sys.modules or not all(os.path.exists(p) for p in libs):
+        return "native fp32 SGEMM (cuBLAS bundled with torch)"
+    os.environ["CUBLAS_EMULATE_SINGLE_PRECISION"] = "1"
+    for p in libs:
+        ctypes.CDLL(p, mode=ctypes.RTLD_GLOBAL)
+    return "cuBLAS 12.9 FP32 emulation BF16x9 (fp32-accurate), fp32 in/out"
+
+
 def run_b200(args):
+    gemm_desc = "native fp32 SGEMM (cuBLAS bundled with torch)"
+    if args.mlp_gemm == "bf16x9":
+        gemm_desc = preload_cublas_fp32_emulation()
     import torch
     import torch.distributed as dist
 
@@ -270,11 +297,11 @@ def run_b200(args):
     fc = [[{"feat": f"I{i}"} for i in range(N_DENSE)],
           [{"feat": f"C{i}", "feat_num": r, "embed_dim": EMBED_DIM} for i, r in enumerate(CRITEO_ROWS)]]
     if world == 1:
-        model = pkg.DLRM(fc, BOT_MLP, TOP_MLP, interaction="dot", seed=1234)
+        model = pkg.DLRM(fc, BOT_MLP, TOP_MLP, interaction="dot", seed=1234, pad_to=args.pad_to)
         trainer = pkg.DLRMTrainer(model, lr=1e-3)
     else:
         from recommend_tf2_b200.sharded import ShardedDLRM, ShardedDLRMTrainer
-        model = ShardedDLRM(fc, BOT_MLP, TOP_MLP, seed=1234)
+        model = ShardedDLRM(fc, BOT_MLP, TOP_MLP, seed=1234, pad_to=args.pad_to)
         trainer = ShardedDLRMTrainer(model, lr=1e-3)
 
     host = make_batches(W + K, B, CRITEO_ROWS, args.ids, seed=1000 + rank)
@@ -345,7 +372,9 @@ def run_b200(args):
                 "unit": "samples/s", "n_gpus": world, "steps": K, "warmup": W,
                 "ms_per_step": ms_total / K, "higher_is_better": True, "scaling": "weak",
                 "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-                "config": bench_config(args, world), "clocks": clocks,
+                "config": dict(bench_config(args, world), mlp_gemm=gemm_desc,
+                               interaction_cols=pkg.dot_out_cols(len(CRITEO_ROWS) + 1, EMBED_DIM, args.pad_to)),
+                "clocks": clocks,
                 "e2e": {"value": B * world * K / (ms_e2e * 1e-3), "unit": "samples/s",
                         "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 4,
                         "ms_per_step": ms_e2e / K},
