@@ -124,6 +124,7 @@ class Dense(Layer):
         super().__init__(**kwargs)
         self.units, self.use_bias, self.kernel_regularizer = units, use_bias, kernel_regularizer
         self.activation = get_activation(activation)
+        self._act_name = activation if isinstance(activation, str) else None
         if isinstance(activation, torch.nn.Module):
             self.activation_module = activation
 
@@ -133,10 +134,35 @@ class Dense(Layer):
         self.bias = self.add_weight("bias", (self.units,), "zeros") if self.use_bias else None
 
     def call(self, x, **kwargs):
+        if self.bias is not None and x.dim() == 2 and x.is_cuda:
+            if self._act_name == "relu":
+                return _DenseBiasRelu.apply(x, self.kernel, self.bias)
+            y = torch.addmm(self.bias, x, self.kernel)           # bias in the GEMM epilogue
+            return self.activation(y) if self.activation is not None else y
         y = torch.matmul(x, self.kernel)
         if self.bias is not None:
             y = y + self.bias
         return self.activation(y) if self.activation is not None else y
+
+
+class _DenseBiasRelu(torch.autograd.Function):
+    """relu(x W + b) with bias and ReLU in the library GEMM's epilogue (one pass over the
+    output instead of three); backward masks the incoming gradient once and reuses it."""
+
+    @staticmethod
+    def forward(ctx, x, w, b):
+        y = torch._addmm_activation(b, x, w, use_gelu=False)
+        ctx.save_for_backward(x, w, y)
+        return y
+
+    @staticmethod
+    def backward(ctx, gy):
+        x, w, y = ctx.saved_tensors
+        g = torch.ops.aten.threshold_backward(gy, y, 0.0)
+        gx = g @ w.t() if ctx.needs_input_grad[0] else None
+        gw = x.t() @ g if ctx.needs_input_grad[1] else None
+        gb = g.sum(0) if ctx.needs_input_grad[2] else None
+        return gx, gw, gb
 
 
 class BatchNormalization(Layer):
