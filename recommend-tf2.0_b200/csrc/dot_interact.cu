@@ -13,6 +13,8 @@
 // a warp hit distinct banks.  Backward re-gathers X (cheaper than saving it) and forms
 // dX = (S + S^T) X with lanes owning 4 embedding columns each.
 // Bound: HBM (ids + rows in, D+P floats out) with the fp32 FMA pipe close behind.
+#include <cstdlib>
+
 #include "rtf_common.cuh"
 
 namespace rtf {
@@ -112,11 +114,13 @@ dot_fwd_kernel(const __grid_constant__ DotParams P, int warp_floats) {
       int bi, bj;
       tri_block(blk, bi, bj);
       // block (bi,bj) covers rows {bi + r*nbr} x {bj + c*nbr}
-      float acc[4][4];
+      // packed fp32x2 FMAs (sm_100 FFMA2): half the issue slots of scalar FFMA; the two halves
+      // of a pair accumulate even / odd pairs of d and are added at the end
+      float2 acc[4][4];
 #pragma unroll
       for (int r = 0; r < 4; ++r)
 #pragma unroll
-        for (int c = 0; c < 4; ++c) acc[r][c] = 0.f;
+        for (int c = 0; c < 4; ++c) acc[r][c] = make_float2(0.f, 0.f);
       const float* pa = xt + bi * RS;
       const float* pb = xt + bj * RS;
       const int rstep = nbr * RS;
@@ -132,10 +136,8 @@ dot_fwd_kernel(const __grid_constant__ DotParams P, int warp_floats) {
         for (int r = 0; r < 4; ++r)
 #pragma unroll
           for (int c = 0; c < 4; ++c) {
-            acc[r][c] = fmaf(a[r].x, q[c].x, acc[r][c]);
-            acc[r][c] = fmaf(a[r].y, q[c].y, acc[r][c]);
-            acc[r][c] = fmaf(a[r].z, q[c].z, acc[r][c]);
-            acc[r][c] = fmaf(a[r].w, q[c].w, acc[r][c]);
+            acc[r][c] = __ffma2_rn(make_float2(a[r].x, a[r].y), make_float2(q[c].x, q[c].y), acc[r][c]);
+            acc[r][c] = __ffma2_rn(make_float2(a[r].z, a[r].w), make_float2(q[c].z, q[c].w), acc[r][c]);
           }
       }
 #pragma unroll
@@ -143,8 +145,9 @@ dot_fwd_kernel(const __grid_constant__ DotParams P, int warp_floats) {
 #pragma unroll
         for (int c = 0; c < 4; ++c) {
           const int i = bi + r * nbr, j = bj + c * nbr;
-          if (i < F1 && j < i) zst[i * (i - 1) / 2 + j] = acc[r][c];
-          else if (bi != bj && j < F1 && i < j) zst[j * (j - 1) / 2 + i] = acc[r][c];
+          const float z = acc[r][c].x + acc[r][c].y;
+          if (i < F1 && j < i) zst[i * (i - 1) / 2 + j] = z;
+          else if (bi != bj && j < F1 && i < j) zst[j * (j - 1) / 2 + i] = z;
         }
     }
     __syncwarp();
@@ -207,6 +210,8 @@ dot_bwd_kernel(const __grid_constant__ DotParams P, int warp_floats) {
     parity ^= 1;
     for (int d0 = lane * 4; d0 < D; d0 += 128) {
       for (int i0 = 0; i0 < F1; i0 += 8) {
+        // (packed FFMA2 with a duplicated {s,s} operand was measured slower here: the doubled S
+        //  tile costs two warps of occupancy and twice the shared loads)
         float4 acc[8];
 #pragma unroll
         for (int r = 0; r < 8; ++r) acc[r] = make_float4(0.f, 0.f, 0.f, 0.f);
@@ -245,6 +250,239 @@ dot_bwd_kernel(const __grid_constant__ DotParams P, int warp_floats) {
   }
 }
 
+// ------------------------------------------------------------------------------------------
+// Tensor-core variants for F1 <= 32, D % 8 == 0 (the DLRM shape: 27 x 128).
+//
+// The FFMA kernels above are bound by instruction issue (ncu: issue slots 59 %, FMA pipe 37 %,
+// DRAM 15 %: 3 458 warp instructions per sample for 1 404 useful FFMA).  A single-pass TF32 MMA
+// would break the 1e-5 fp32 parity bar, so each operand is split x = hi + lo (two TF32 values,
+// ~22 mantissa bits) and every product is three m16n8k8 MMAs (hi*hi + hi*lo + lo*hi, fp32
+// accumulate) — "3xTF32", error ~2^-21 of |x_i||x_j|.  The per-sample Gram (M = N = 32) is far
+// below tcgen05's M >= 64 tile, so this is warp-level mma.sync (one warp still owns one sample,
+// rows still arrive by TMA bulk copies); ~4x fewer issue slots than the FFMA form.
+// Fragment trick: for Z = X X^T the B fragment of an 8-row n-tile is a relabelling of the A
+// fragment registers of the 16-row m-tile that contains it, so X is read from shared memory once.
+__device__ __forceinline__ uint32_t f2tf32(float x) {
+  uint32_t r;
+  asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(x));
+  return r;
+}
+__device__ __forceinline__ void split_tf32(float x, uint32_t& hi, uint32_t& lo) {
+  hi = f2tf32(x);
+  lo = f2tf32(x - __uint_as_float(hi));
+}
+__device__ __forceinline__ void mma_tf32(float (&c)[4], const uint32_t (&a)[4], uint32_t b0,
+                                         uint32_t b1) {
+  asm volatile(
+      "mma.sync.aligned.m16n8k8.row.col.f32.tf32.tf32.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, "
+      "{%0,%1,%2,%3};"
+      : "+f"(c[0]), "+f"(c[1]), "+f"(c[2]), "+f"(c[3])
+      : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
+}
+// c += A*B with A, B given as hi/lo pairs (small terms first)
+__device__ __forceinline__ void mma3(float (&c)[4], const uint32_t (&ah)[4], const uint32_t (&al)[4],
+                                     uint32_t bh0, uint32_t bh1, uint32_t bl0, uint32_t bl1) {
+  mma_tf32(c, al, bh0, bh1);
+  mma_tf32(c, ah, bl0, bl1);
+  mma_tf32(c, ah, bh0, bh1);
+}
+
+__host__ __device__ inline int dot_row_stride_bwd(int D) { return D + ((D % 32 == 24) ? 16 : 8); }
+
+template <typename IdT>
+__global__ void __launch_bounds__(512, 1)
+dot_fwd_mma_kernel(const __grid_constant__ DotParams P, int warp_floats) {
+  extern __shared__ __align__(16) float smem[];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
+  const int g = lane >> 2, t = lane & 3;
+  const int F1 = P.F1, D = P.D;
+  const int RS = dot_row_stride(D);
+  const int npairs = F1 * (F1 - 1) / 2;
+  float* xt = smem + (size_t)warp * warp_floats;  // [32][RS], rows >= F1 stay zero
+  float* zst = xt + 32 * RS;
+  uint64_t* bar = reinterpret_cast<uint64_t*>(zst + ((npairs + 3) & ~3));
+  if (lane == 0) {
+    mbar_init(bar, 1);
+    mbar_fence_init();
+  }
+  for (int i = F1 * RS + lane; i < 32 * RS; i += 32) xt[i] = 0.f;
+  __syncwarp();
+  const long long stride = (long long)gridDim.x * nwarps;
+  long long b = (long long)blockIdx.x * nwarps + warp;
+  uint32_t parity = 0;
+  if (b < P.B) dot_issue_rows<IdT>(P, b, xt, RS, bar, lane);
+  const bool two_mt = F1 > 16;
+
+  for (; b < P.B; b += stride) {
+    mbar_wait(bar, parity);
+    parity ^= 1;
+    // tiles (m-tile, n-tile): (0,0) (0,1) (1,0) (1,1) (1,2) (1,3)
+    float acc[6][4];
+#pragma unroll
+    for (int i = 0; i < 6; ++i)
+#pragma unroll
+      for (int j = 0; j < 4; ++j) acc[i][j] = 0.f;
+    const float* r0 = xt + g * RS + t;
+#pragma unroll 2
+    for (int k0 = 0; k0 < D; k0 += 8) {
+      uint32_t ah[2][4], al[2][4];
+#pragma unroll
+      for (int mt = 0; mt < 2; ++mt) {
+        if (mt == 1 && !two_mt) {
+#pragma unroll
+          for (int q = 0; q < 4; ++q) ah[1][q] = al[1][q] = 0u;
+          continue;
+        }
+        const float* p = r0 + mt * 16 * RS + k0;
+        split_tf32(p[0], ah[mt][0], al[mt][0]);
+        split_tf32(p[8 * RS], ah[mt][1], al[mt][1]);
+        split_tf32(p[4], ah[mt][2], al[mt][2]);
+        split_tf32(p[8 * RS + 4], ah[mt][3], al[mt][3]);
+      }
+      // n-tile nt of 8 rows: nt = 2*mt' + h  ->  B regs = A regs (h, h+2) of m-tile mt'
+      mma3(acc[0], ah[0], al[0], ah[0][0], ah[0][2], al[0][0], al[0][2]);
+      mma3(acc[1], ah[0], al[0], ah[0][1], ah[0][3], al[0][1], al[0][3]);
+      if (two_mt) {
+        mma3(acc[2], ah[1], al[1], ah[0][0], ah[0][2], al[0][0], al[0][2]);
+        mma3(acc[3], ah[1], al[1], ah[0][1], ah[0][3], al[0][1], al[0][3]);
+        mma3(acc[4], ah[1], al[1], ah[1][0], ah[1][2], al[1][0], al[1][2]);
+        mma3(acc[5], ah[1], al[1], ah[1][1], ah[1][3], al[1][1], al[1][3]);
+      }
+    }
+    // scatter the lower triangle into the staging row: c0 (g,2t) c1 (g,2t+1) c2 (g+8,2t) c3 (g+8,2t+1)
+#pragma unroll
+    for (int tile = 0; tile < 6; ++tile) {
+      const int mt = tile < 2 ? 0 : 1, nt = tile < 2 ? tile : tile - 2;
+#pragma unroll
+      for (int q = 0; q < 4; ++q) {
+        const int i = mt * 16 + g + ((q & 2) ? 8 : 0);
+        const int j = nt * 8 + 2 * t + (q & 1);
+        if (i < F1 && j < i) zst[i * (i - 1) / 2 + j] = acc[tile][q];
+      }
+    }
+    __syncwarp();
+    float* o = P.out + b * P.out_sb;
+    for (int d = lane; d < D; d += 32) o[d] = xt[d];
+    for (int p = lane; p < npairs; p += 32) o[D + p] = zst[p];
+    for (int p = D + npairs + lane; p < P.out_cols; p += 32) o[p] = 0.f;
+    __syncwarp();
+    if (b + stride < P.B) dot_issue_rows<IdT>(P, b + stride, xt, RS, bar, lane);
+  }
+}
+
+template <typename IdT>
+__global__ void __launch_bounds__(512, 1)
+dot_bwd_mma_kernel(const __grid_constant__ DotParams P, int warp_floats) {
+  extern __shared__ __align__(16) float smem[];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
+  const int g = lane >> 2, t = lane & 3;
+  const int F1 = P.F1, D = P.D;
+  const int RS = dot_row_stride_bwd(D);
+  constexpr int SS = 36;  // S row stride: 4g + t hits 32 distinct banks
+  const int npairs = F1 * (F1 - 1) / 2;
+  unsigned short* pair_ij = reinterpret_cast<unsigned short*>(smem);
+  const int pair_floats = ((npairs + 1) / 2 + 3) & ~3;
+  float* xt = smem + pair_floats + (size_t)warp * warp_floats;  // [32][RS]
+  float* S = xt + 32 * RS;                                      // [32][SS]
+  uint64_t* bar = reinterpret_cast<uint64_t*>(S + 32 * SS);
+  for (int p = threadIdx.x; p < npairs; p += blockDim.x) {
+    int i = (int)((1.f + sqrtf(1.f + 8.f * p)) * 0.5f);
+    while (i * (i - 1) / 2 > p) --i;
+    while ((i + 1) * i / 2 <= p) ++i;
+    pair_ij[p] = (unsigned short)((i << 8) | (p - i * (i - 1) / 2));
+  }
+  if (lane == 0) {
+    mbar_init(bar, 1);
+    mbar_fence_init();
+  }
+  for (int i = F1 * RS + lane; i < 32 * RS; i += 32) xt[i] = 0.f;
+  for (int i = lane; i < 32 * SS; i += 32) S[i] = 0.f;
+  __syncthreads();
+  const long long stride = (long long)gridDim.x * nwarps;
+  long long b = (long long)blockIdx.x * nwarps + warp;
+  uint32_t parity = 0;
+  if (b < P.B) dot_issue_rows<IdT>(P, b, xt, RS, bar, lane);
+  const int n_mt = F1 > 16 ? 2 : 1;
+  const int n_ks = (F1 + 7) >> 3;
+
+  for (; b < P.B; b += stride) {
+    const float* gr = P.gout + b * P.gout_sb;
+    for (int p = lane; p < npairs; p += 32) {
+      const float v = __ldg(gr + D + p);
+      const int ij = pair_ij[p];
+      const int i = ij >> 8, j = ij & 255;
+      S[i * SS + j] = v;
+      S[j * SS + i] = v;
+    }
+    __syncwarp();
+    // A fragments of S (hi/lo), kept in registers for the whole sample
+    uint32_t sh[2][4][4], sl[2][4][4];
+#pragma unroll
+    for (int mt = 0; mt < 2; ++mt)
+#pragma unroll
+      for (int ks = 0; ks < 4; ++ks) {
+        const float* p = S + (mt * 16 + g) * SS + ks * 8 + t;
+        split_tf32(p[0], sh[mt][ks][0], sl[mt][ks][0]);
+        split_tf32(p[8 * SS], sh[mt][ks][1], sl[mt][ks][1]);
+        split_tf32(p[4], sh[mt][ks][2], sl[mt][ks][2]);
+        split_tf32(p[8 * SS + 4], sh[mt][ks][3], sl[mt][ks][3]);
+      }
+    mbar_wait(bar, parity);
+    parity ^= 1;
+    for (int n0 = 0; n0 < D; n0 += 32) {  // 4 n-tiles of 8 columns per chunk
+      float acc[2][4][4];
+#pragma unroll
+      for (int mt = 0; mt < 2; ++mt)
+#pragma unroll
+        for (int nt = 0; nt < 4; ++nt)
+#pragma unroll
+          for (int q = 0; q < 4; ++q) acc[mt][nt][q] = 0.f;
+#pragma unroll
+      for (int ks = 0; ks < 4; ++ks) {
+        if (ks >= n_ks) break;
+#pragma unroll
+        for (int nt = 0; nt < 4; ++nt) {
+          const int n = n0 + nt * 8 + g;
+          uint32_t bh0 = 0, bh1 = 0, bl0 = 0, bl1 = 0;
+          if (n < D) {
+            split_tf32(xt[(ks * 8 + t) * RS + n], bh0, bl0);
+            split_tf32(xt[(ks * 8 + t + 4) * RS + n], bh1, bl1);
+          }
+          mma3(acc[0][nt], sh[0][ks], sl[0][ks], bh0, bh1, bl0, bl1);
+          if (n_mt > 1) mma3(acc[1][nt], sh[1][ks], sl[1][ks], bh0, bh1, bl0, bl1);
+        }
+      }
+#pragma unroll
+      for (int mt = 0; mt < 2; ++mt)
+#pragma unroll
+        for (int nt = 0; nt < 4; ++nt)
+#pragma unroll
+          for (int h = 0; h < 2; ++h) {
+            const int i = mt * 16 + g + h * 8;
+            const int c = n0 + nt * 8 + 2 * t;
+            if (i < F1 && c < D) {
+              float2 v = make_float2(acc[mt][nt][2 * h], acc[mt][nt][2 * h + 1]);
+              if (i == 0) {  // out[:, :D] is X[0] itself
+                v.x += __ldg(gr + c);
+                v.y += __ldg(gr + c + 1);
+              }
+              *reinterpret_cast<float2*>(P.gbase[i] + b * P.gstride[i] + c) = v;
+            }
+          }
+    }
+    __syncwarp();
+    if (b + stride < P.B) dot_issue_rows<IdT>(P, b + stride, xt, RS, bar, lane);
+  }
+}
+
+static bool dot_use_mma(int F1, int D) {
+  // measured on B200 (profiles/README.md): legacy mma.sync TF32 runs at ~20 cycles per m16n8k8
+  // per SM sub-partition, so 3xTF32 is no faster than packed FFMA2 forward (0.35 vs 0.38 ms)
+  // and 2x slower backward; opt-in for experiments only.
+  static const bool use_mma = getenv("RTF_DOT_MMA") != nullptr;
+  return use_mma && F1 <= 32 && D % 8 == 0;
+}
+
 static int dot_check_common(long long B, int F1, int D) {
   if (B < 0 || F1 < 2 || D <= 0) return RTF_E_ARG;
   if (F1 > RTF_MAX_FIELDS || D % 4 || D > 1024) return RTF_E_RANGE;
@@ -272,6 +510,11 @@ static int dot_launch(Kern kern, const DotParams& P, int warp_floats, int cta_fl
 static int dot_fwd_impl(DotParams& P, int ids_i64, cudaStream_t st) {
   const int F1p = (P.F1 + 3) & ~3, RS = dot_row_stride(P.D);
   const int npairs = P.F1 * (P.F1 - 1) / 2;
+  if (dot_use_mma(P.F1, P.D)) {
+    const int wf = 32 * RS + ((npairs + 3) & ~3) + 4;
+    return ids_i64 ? dot_launch(dot_fwd_mma_kernel<int64_t>, P, wf, 0, st)
+                   : dot_launch(dot_fwd_mma_kernel<int32_t>, P, wf, 0, st);
+  }
   const int warp_floats = F1p * RS + ((npairs + 3) & ~3) + 4;  // + mbarrier (8 B, 16-B slot)
   return ids_i64 ? dot_launch(dot_fwd_kernel<int64_t>, P, warp_floats, 0, st)
                  : dot_launch(dot_fwd_kernel<int32_t>, P, warp_floats, 0, st);
@@ -279,6 +522,12 @@ static int dot_fwd_impl(DotParams& P, int ids_i64, cudaStream_t st) {
 static int dot_bwd_impl(DotParams& P, int ids_i64, cudaStream_t st) {
   const int F1p = (P.F1 + 7) & ~7, RS = dot_row_stride(P.D);
   const int npairs = P.F1 * (P.F1 - 1) / 2;
+  if (dot_use_mma(P.F1, P.D)) {
+    const int wf = 32 * dot_row_stride_bwd(P.D) + 32 * 36 + 4;
+    const int cf = ((npairs + 1) / 2 + 3) & ~3;
+    return ids_i64 ? dot_launch(dot_bwd_mma_kernel<int64_t>, P, wf, cf, st)
+                   : dot_launch(dot_bwd_mma_kernel<int32_t>, P, wf, cf, st);
+  }
   const int warp_floats = P.F1 * RS + F1p * F1p + 4;
   const int cta_floats = ((npairs + 1) / 2 + 3) & ~3;
   return ids_i64 ? dot_launch(dot_bwd_kernel<int64_t>, P, warp_floats, cta_floats, st)
