@@ -135,34 +135,46 @@ class Dense(Layer):
 
     def call(self, x, **kwargs):
         if self.bias is not None and x.dim() == 2 and x.is_cuda:
-            if self._act_name == "relu":
-                return _DenseBiasRelu.apply(x, self.kernel, self.bias)
-            y = torch.addmm(self.bias, x, self.kernel)           # bias in the GEMM epilogue
-            return self.activation(y) if self.activation is not None else y
+            relu = self._act_name == "relu"
+            y = _DenseFn.apply(x, self.kernel, self.bias, relu)
+            return y if (relu or self.activation is None) else self.activation(y)
         y = torch.matmul(x, self.kernel)
         if self.bias is not None:
             y = y + self.bias
         return self.activation(y) if self.activation is not None else y
 
 
-class _DenseBiasRelu(torch.autograd.Function):
-    """relu(x W + b) with bias and ReLU in the library GEMM's epilogue (one pass over the
-    output instead of three); backward masks the incoming gradient once and reuses it."""
+def _wgrad(x: torch.Tensor, g: torch.Tensor) -> torch.Tensor:
+    """dW = x^T g for a tall batch.  The reduction runs over the batch (K = 65 536 here) while the
+    output is only a few 128x128 tiles, so a single library GEMM leaves most SMs idle; a batched
+    split-K (fixed chunking, partials summed in order => deterministic) measured 2-2.6x faster
+    (tools/probe_wgrad.py)."""
+    B = x.shape[0]
+    S = 16
+    if B >= 8192 and B % S == 0 and x.is_contiguous() and g.is_contiguous():
+        return torch.bmm(x.view(S, B // S, -1).transpose(1, 2), g.view(S, B // S, -1)).sum(0)
+    return x.t() @ g
+
+
+class _DenseFn(torch.autograd.Function):
+    """x W + b (optionally ReLU) with bias / ReLU in the library GEMM's epilogue — one pass over
+    the output instead of three; backward masks the incoming gradient once, split-K weight grad."""
 
     @staticmethod
-    def forward(ctx, x, w, b):
-        y = torch._addmm_activation(b, x, w, use_gelu=False)
-        ctx.save_for_backward(x, w, y)
+    def forward(ctx, x, w, b, relu):
+        y = torch._addmm_activation(b, x, w, use_gelu=False) if relu else torch.addmm(b, x, w)
+        ctx.save_for_backward(x, w, y if relu else None)
+        ctx.relu = relu
         return y
 
     @staticmethod
     def backward(ctx, gy):
         x, w, y = ctx.saved_tensors
-        g = torch.ops.aten.threshold_backward(gy, y, 0.0)
+        g = torch.ops.aten.threshold_backward(gy, y, 0.0) if ctx.relu else gy.contiguous()
         gx = g @ w.t() if ctx.needs_input_grad[0] else None
-        gw = x.t() @ g if ctx.needs_input_grad[1] else None
+        gw = _wgrad(x, g) if ctx.needs_input_grad[1] else None
         gb = g.sum(0) if ctx.needs_input_grad[2] else None
-        return gx, gw, gb
+        return gx, gw, gb, None
 
 
 class BatchNormalization(Layer):
