@@ -45,6 +45,8 @@ def parse_args():
     ap.add_argument("--mlp-gemm", default="bf16x9", choices=["bf16x9", "native"],
                     help="dense-MLP GEMMs: cuBLAS 12.9 FP32 emulation (BF16x9, fp32-accurate) or SGEMM")
     ap.add_argument("--pad-to", type=int, default=8, help="round the interaction width up (479 -> 480)")
+    ap.add_argument("--exchange", default="p2p", choices=["p2p", "nccl"],
+                    help="multi-GPU row exchange: fused into K4 over NVLink peer memory, or NCCL all-to-all")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-kernel-timing", action="store_true")
     return ap.parse_args()
@@ -143,7 +145,8 @@ def bench_config(args, world):
             "global_batch": args.batch * world, "ids": args.ids,
             "optimizer": "adam (sparse rows fused in K2, dense MLP torch fused)",
             "l2_flush": "inputs larger than L2: 17.2 GB of tables, distinct batch every step",
-            "parallelism": "single" if world == 1 else f"tables sharded over {world} GPUs + dp MLP"}
+            "parallelism": "single" if world == 1 else
+            f"tables sharded over {world} GPUs ({args.exchange} row exchange) + dp MLP"}
 
 
 def run_reference(args):
@@ -301,7 +304,7 @@ def run_b200(args):
         trainer = pkg.DLRMTrainer(model, lr=1e-3)
     else:
         from recommend_tf2_b200.sharded import ShardedDLRM, ShardedDLRMTrainer
-        model = ShardedDLRM(fc, BOT_MLP, TOP_MLP, seed=1234, pad_to=args.pad_to)
+        model = ShardedDLRM(fc, BOT_MLP, TOP_MLP, seed=1234, pad_to=args.pad_to, exchange=args.exchange)
         trainer = ShardedDLRMTrainer(model, lr=1e-3)
 
     host = make_batches(W + K, B, CRITEO_ROWS, args.ids, seed=1000 + rank)

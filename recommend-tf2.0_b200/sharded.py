@@ -161,14 +161,72 @@ class _ShardedInteractFn(torch.autograd.Function):
         return None, gdense, None, None
 
 
+def _peer_row_tables(layout: ShardLayout, peer_ptrs, dense: torch.Tensor, B_local: int, D: int):
+    """Row (base, stride) tables when the rows are read from / written to the OWNERS' buffers
+    over NVLink: rank g's buffer is (B_global, T_g, D) sample-major, so table t (owner g, slot j)
+    of my local sample b sits at peer_ptrs[g] + ((me*B_local + b)*T_g + j)*D."""
+    me = layout.rank
+    base = [dense.data_ptr()]
+    stride = [dense.stride(0)]
+    for t in range(layout.n_tables):
+        g, j = layout.slot_of[t]
+        Tg = layout.T[g]
+        base.append(peer_ptrs[g] + (me * B_local * Tg + j) * D * 4)
+        stride.append(Tg * D)
+    return (C.c_void_p * len(base))(*base), (C.c_int64 * len(stride))(*stride)
+
+
+class _PeerInteractFn(torch.autograd.Function):
+    """K4 fused with the exchange over NVLink peer memory (no NCCL all-to-all): the forward's
+    TMA bulk copies pull each embedding row straight from its owner's HBM, the backward re-pulls
+    them and stores the dX rows straight into the owners' gradient buffers.  The transfer is
+    overlapped with the Gram arithmetic row by row inside the one kernel."""
+
+    @staticmethod
+    def forward(ctx, model: "ShardedDLRM", dense, pad_to):
+        dense = dense.contiguous()
+        lay = model.layout
+        B, D = dense.shape
+        F1 = lay.n_tables + 1
+        cols = dot_out_cols(F1, D, pad_to)
+        out = torch.empty((B, cols), dtype=torch.float32, device=dense.device)
+        rb, rs = _peer_row_tables(lay, model._out_hdl.buffer_ptrs, dense, B, D)
+        L.check(L.lib().rtf_dot_rows_fwd(rb, rs, F1, D, B, out.data_ptr(), cols, cols,
+                                         L.current_stream_ptr()), "rtf_dot_rows_fwd")
+        ctx.model = model
+        ctx.save_for_backward(dense)
+        return out
+
+    @staticmethod
+    def backward(ctx, gout):
+        (dense,) = ctx.saved_tensors
+        model = ctx.model
+        lay = model.layout
+        gout = gout.contiguous()
+        B, D = dense.shape
+        F1 = lay.n_tables + 1
+        gdense = torch.empty_like(dense)
+        rb, rs = _peer_row_tables(lay, model._out_hdl.buffer_ptrs, dense, B, D)
+        gb, gs = _peer_row_tables(lay, model._grad_hdl.buffer_ptrs, gdense, B, D)
+        L.check(L.lib().rtf_dot_rows_bwd(rb, rs, F1, D, B, gout.data_ptr(), gout.stride(0), gb, gs,
+                                         L.current_stream_ptr()), "rtf_dot_rows_bwd")
+        model._pending = "p2p"
+        return None, gdense, None
+
+
 class ShardedDLRM(Layer):
     """DLRM (same constructor as dlrm.DLRM) with table-wise sharded embeddings."""
 
     def __init__(self, feature_columns, bot_dnn_hidden_units=(64, 32, 16),
                  top_dnn_hidden_units=(128, 64), activation="relu", dnn_dropout=0.0, embed_reg=1e-4,
                  sparse_optimizer: Optional[SparseOptimizer] = None, pad_to: int = 1,
-                 input_bn: bool = True, seed: Optional[int] = None, owners=None):
+                 input_bn: bool = True, seed: Optional[int] = None, owners=None,
+                 exchange: str = "p2p"):
         super().__init__()
+        if exchange not in ("p2p", "nccl"):
+            raise ValueError(exchange)
+        self.exchange = exchange
+        self._sym_B = None
         self.world, self.rank = dist.get_world_size(), dist.get_rank()
         self.dense_feature_columns, self.sparse_feature_columns = feature_columns
         rows = [f["feat_num"] for f in self.sparse_feature_columns]
@@ -198,19 +256,56 @@ class ShardedDLRM(Layer):
         B_local = sparse_inputs.shape[0]
         ids_global = exchange_ids(sparse_inputs, self.world)                       # (B_global, F)
         local_ids = ids_global.index_select(1, self._mine_idx).contiguous()        # (B_global, T_me)
+        self._saved = local_ids
+        if self.exchange == "p2p":
+            return self._call_p2p(dense_inputs, local_ids, B_local)
         with torch.no_grad():
             local_out = embed_fwd(list(self.embed_layers.weights), local_ids, "BF", None,
                                   err=self.embed_layers.err)
         recv, work = exchange_rows_fwd(local_out, lay, B_local, D, async_op=True)
         dense_fea = self.bot_dnn(dense_inputs)            # overlaps the all-to-all
         work.wait()
-        self._saved = local_ids
         x = _ShardedInteractFn.apply(self, dense_fea, recv, self.pad_to)
+        return torch.sigmoid(self.final_dense(self.top_dnn(x)))
+
+    # ---- exchange over NVLink peer memory (torch symmetric memory for the address exchange)
+    def _ensure_symmetric(self, B_local: int):
+        if self._sym_B == B_local:
+            return
+        import torch.distributed._symmetric_memory as symm
+        n = B_local * self.world * max(self.layout.T) * self.D       # same size on every rank
+        dev = self.embed_layers.err.device
+        self._out_buf = symm.empty(n, dtype=torch.float32, device=dev)
+        self._grad_buf = symm.empty(n, dtype=torch.float32, device=dev)
+        self._out_hdl = symm.rendezvous(self._out_buf, dist.group.WORLD)
+        self._grad_hdl = symm.rendezvous(self._grad_buf, dist.group.WORLD)
+        self._sym_B = B_local
+
+    def _call_p2p(self, dense_inputs, local_ids, B_local):
+        self._ensure_symmetric(B_local)
+        D, Tme = self.D, self.layout.T[self.rank]
+        Bg = B_local * self.world
+        out_view = self._out_buf[: Bg * Tme * D].view(Bg, Tme * D)
+        with torch.no_grad():
+            embed_fwd(list(self.embed_layers.weights), local_ids, "BF", None,
+                      err=self.embed_layers.err, out=out_view)
+        dense_fea = self.bot_dnn(dense_inputs)
+        self._out_hdl.barrier(channel=0)      # every owner's rows are in place (stream-ordered)
+        x = _PeerInteractFn.apply(self, dense_fea, self.pad_to)
         return torch.sigmoid(self.final_dense(self.top_dnn(x)))
 
     def finish_backward(self):
         """Wait for the reverse exchange and run K2 (+ fused sparse optimizer) on the owner."""
         if self._pending is None:
+            return
+        if self._pending == "p2p":
+            self._grad_hdl.barrier(channel=0)  # all peers' dX rows have landed in my buffer
+            D, Tme = self.D, self.layout.T[self.rank]
+            Bg = self._sym_B * self.world
+            grecv = self._grad_buf[: Bg * Tme * D].view(Bg, Tme * D)
+            self.embed_layers.apply_sparse_grad(self._saved,
+                                                list(range(len(self.embed_layers.weights))), grecv)
+            self._pending = None
             return
         grecv, work, _keep = self._pending
         work.wait()

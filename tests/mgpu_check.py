@@ -21,8 +21,9 @@ def main():
     fc = [[{"feat": f"I{i}"} for i in range(13)],
           [{"feat": f"C{t}", "feat_num": rows[t], "embed_dim": D} for t in range(F)]]
     kw = dict(bot_dnn_hidden_units=(64, D), top_dnn_hidden_units=(128, 64), input_bn=False)
+    mode = os.environ.get("RTF_EXCHANGE", "p2p")
     single = pkg.DLRM(fc, seed=5, **kw)
-    sharded = ShardedDLRM(fc, seed=5, **kw)
+    sharded = ShardedDLRM(fc, seed=5, exchange=mode, **kw)
     g = torch.Generator(device="cuda").manual_seed(99)
     B = B_local * world
     dense = torch.rand(B, 13, device="cuda", generator=g)
@@ -58,7 +59,7 @@ def main():
     sharded.embed_layers.check_ids()
     dist.barrier()
     if rank == 0:
-        print(f"mgpu_check ok: world={world} owners={sharded.layout.owners}")
+        print(f"mgpu_check ok: world={world} exchange={mode} owners={sharded.layout.owners}")
     dist.destroy_process_group()
 
 
