@@ -221,7 +221,7 @@ class ShardedDLRM(Layer):
                  top_dnn_hidden_units=(128, 64), activation="relu", dnn_dropout=0.0, embed_reg=1e-4,
                  sparse_optimizer: Optional[SparseOptimizer] = None, pad_to: int = 1,
                  input_bn: bool = True, seed: Optional[int] = None, owners=None,
-                 exchange: str = "p2p"):
+                 exchange: str = "nccl"):
         super().__init__()
         if exchange not in ("p2p", "nccl"):
             raise ValueError(exchange)
