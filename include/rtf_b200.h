@@ -97,6 +97,22 @@ int rtf_embed_bwd(float* const* weights, float* const* state1, float* const* sta
                   uint32_t* d_uniq_key, float* d_uniq_grad, int32_t* d_num_uniq,
                   int* row_bits_out, void* d_workspace, size_t workspace_bytes, void* stream);
 
+/* K2 in two halves, so that the id-only work (keys, sort, segments) can run on a side stream
+ * while the forward/backward of the dense part is still computing, and only the gradient-
+ * dependent half sits on the critical path.  _prepare fills the workspace; _apply consumes it
+ * ONCE (same rows/dims/field_table/B/L, same workspace).  rtf_embed_bwd == prepare + apply.   */
+int rtf_embed_bwd_prepare(const int64_t* rows, const int32_t* dims, int n_tables,
+                          const int32_t* field_table, int n_fields, const void* d_ids,
+                          int ids_i64, int64_t B, int L, int64_t ids_sb, int64_t ids_sf,
+                          int64_t ids_sl, int32_t* d_num_uniq, int* row_bits_out,
+                          void* d_workspace, size_t workspace_bytes, void* stream);
+int rtf_embed_bwd_apply(float* const* weights, float* const* state1, float* const* state2,
+                        const int64_t* rows, const int32_t* dims, int n_tables,
+                        const int32_t* field_table, int n_fields, int64_t B, int L, int pool,
+                        const float* d_grad, int64_t grad_sb, const rtf_opt* opt,
+                        uint32_t* d_uniq_key, float* d_uniq_grad, void* d_workspace,
+                        size_t workspace_bytes, void* stream);
+
 /* ---- K4: DLRM pairwise dot interaction ------------------------------------------
  * replaces: the missing interaction at src/ctr/dlrm/model.py:48 (the file concatenates;
  *           the op is defined from the paper it cites at :7)

@@ -43,6 +43,10 @@ SIGNATURES = {
     "rtf_embed_bwd": [_p, _p, _p, _p, _p, _int, _p, _int, _p, _int, _i64, _int, _i64, _i64,
                       _i64, _int, _p, _i64, C.POINTER(rtf_opt), _p, _p, _p,
                       C.POINTER(C.c_int), _p, C.c_size_t, _p],
+    "rtf_embed_bwd_prepare": [_p, _p, _int, _p, _int, _p, _int, _i64, _int, _i64, _i64, _i64, _p,
+                              C.POINTER(C.c_int), _p, C.c_size_t, _p],
+    "rtf_embed_bwd_apply": [_p, _p, _p, _p, _p, _int, _p, _int, _i64, _int, _int, _p, _i64,
+                            C.POINTER(rtf_opt), _p, _p, _p, C.c_size_t, _p],
     "rtf_dot_interact_fwd": [_p, _i64, _int, _int, _p, _i64, _int, _p],
     "rtf_dot_interact_bwd": [_p, _p, _i64, _i64, _int, _int, _p, _p],
     "rtf_dot_rows_fwd": [_p, _p, _int, _int, _i64, _p, _i64, _int, _p],

@@ -215,6 +215,51 @@ class EmbeddingTables(torch.nn.Module):
             field_table = list(range(len(self.weights)))
         return _LookupFn.apply(self, ids, tuple(field_table), layout, pool, *self.weights)
 
+    # ---- K2 split: id-only half on a side stream, gradient half on the critical path
+    def prepare_backward(self, ids, field_table, layout="BF"):
+        """Launch keys + sort + segments for this batch on a side stream (they depend on the ids
+        only) so they overlap the dense forward/backward; returns a handle for apply_prepared."""
+        lib = L.lib()
+        B, F, Lq, sb, sf, sl = ids_strides(ids, layout)
+        rows = [int(w.shape[0]) for w in self.weights]
+        dims = [int(w.shape[1]) for w in self.weights]
+        n = B * F * Lq
+        nbytes = C.c_size_t(0)
+        L.check(lib.rtf_embed_bwd_workspace(n, max(dims), C.byref(nbytes)), "rtf_embed_bwd_workspace")
+        ws = torch.empty(max(nbytes.value, 16), dtype=torch.uint8, device=ids.device)
+        cur = torch.cuda.current_stream()
+        if getattr(self, "_side", None) is None:
+            self._side = torch.cuda.Stream()
+        side = self._side
+        side.wait_stream(cur)
+        with torch.cuda.stream(side):
+            rc = lib.rtf_embed_bwd_prepare(L.host_array(C.c_int64, rows), L.host_array(C.c_int32, dims),
+                                           len(rows), L.host_array(C.c_int32, list(field_table)), F,
+                                           ids.data_ptr(), int(ids.dtype == torch.int64), B, Lq, sb, sf,
+                                           sl, None, None, ws.data_ptr(), ws.numel(), side.cuda_stream)
+            L.check(rc, "rtf_embed_bwd_prepare")
+            ev = torch.cuda.Event()
+            ev.record(side)
+        ws.record_stream(side)
+        ids.record_stream(side)
+        return {"ws": ws, "ev": ev, "B": B, "F": F, "L": Lq, "field_table": tuple(field_table)}
+
+    def apply_prepared(self, h, grad, pool=None):
+        lib = L.lib()
+        opt = self.optimizer
+        st = opt.struct_for_step(max(opt.step, 1))
+        rows = [int(w.shape[0]) for w in self.weights]
+        dims = [int(w.shape[1]) for w in self.weights]
+        torch.cuda.current_stream().wait_event(h["ev"])
+        rc = lib.rtf_embed_bwd_apply(_ptr_array([w.data for w in self.weights]), _ptr_array(self.state1),
+                                     _ptr_array(self.state2), L.host_array(C.c_int64, rows),
+                                     L.host_array(C.c_int32, dims), len(rows),
+                                     L.host_array(C.c_int32, list(h["field_table"])), h["F"], h["B"],
+                                     h["L"], _POOL[pool], grad.data_ptr(), grad.stride(0),
+                                     C.byref(st), None, None, h["ws"].data_ptr(), h["ws"].numel(),
+                                     L.current_stream_ptr())
+        L.check(rc, "rtf_embed_bwd_apply")
+
     def apply_sparse_grad(self, ids, field_table, grad, layout="BF", pool=None):
         opt = self.optimizer
         step = max(opt.step, 1)

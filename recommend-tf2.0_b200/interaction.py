@@ -70,6 +70,11 @@ class _EmbedDotFn(torch.autograd.Function):
                                        L.current_stream_ptr())
         L.check(rc, "rtf_embed_dot_fwd")
         ctx.tset, ctx.ids, ctx.field_table = tset, ids, field_table
+        # the id-only half of K2 (keys, sort, segments) starts now on a side stream and hides
+        # behind the top MLP; the backward then only runs the gradient-dependent half
+        ctx.prepared = None
+        if tset.optimizer is not None and any(ctx.needs_input_grad):
+            ctx.prepared = tset.prepare_backward(ids, field_table)
         ctx.save_for_backward(dense)
         return out
 
@@ -91,6 +96,9 @@ class _EmbedDotFn(torch.autograd.Function):
                                        gdense.stride(0), gemb.data_ptr(), gemb.stride(0),
                                        L.current_stream_ptr())
         L.check(rc, "rtf_embed_dot_bwd")
+        if ctx.prepared is not None:
+            tset.apply_prepared(ctx.prepared, gemb)
+            return (None, None, None, None, gdense) + (None,) * len(tset.weights)
         wgrads = tset.grads_from_lookup_grad(ids, field_table, gemb, "BF", None)
         return (None, None, None, None, gdense) + wgrads
 
