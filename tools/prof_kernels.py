@@ -25,9 +25,12 @@ def main():
     ap.add_argument("--iters", type=int, default=3)
     ap.add_argument("--which", default="k1,fwd,bwd,k2")
     ap.add_argument("--ids", default="uniform")
+    ap.add_argument("--row-cap", type=int, default=10_000_000,
+                    help="cap table rows (ncu --set full saves/restores every buffer a kernel writes)")
     a = ap.parse_args()
     which = set(a.which.split(","))
-    rows, D, F, B = bench.CRITEO_ROWS, bench.EMBED_DIM, len(bench.CRITEO_ROWS), a.batch
+    rows = [min(r, a.row_cap) for r in bench.CRITEO_ROWS]
+    D, F, B = bench.EMBED_DIM, len(rows), a.batch
     ts = pkg.EmbeddingTables(rows, [D] * F, seed=1, optimizer=pkg.SparseOptimizer("adam"))
     ts.begin_step()
     batches = [b[1].cuda() for b in bench.make_batches(a.iters, B, rows, a.ids, seed=7)]
