@@ -10,10 +10,11 @@
 //
 // The tiled q and the (B,L,4d) `info` tensor are never built:
 //   info_l . W = (W1+W3).q + (W2-W3 + W4*q).k_l = c + u.k_l
-// so a sample needs one pass over its k/v rows.  One warp per sample; its (L,d) key tile (and
-// value tile when v is a different tensor) is staged in shared memory by a single TMA bulk copy
-// (SASS UBLKCP) on a per-warp mbarrier; scores use lane-groups over d with shuffle reductions
-// (conflict-free shared reads), the softmax and the a.v product run out of shared memory.
+// so a sample needs one pass over its k/v rows.  One 4-warp CTA per sample; its (L,d) key tile
+// (and value tile when v is a different tensor) is staged in shared memory by a single TMA bulk
+// copy (SASS UBLKCP) on the CTA's mbarrier; rows are split across the warps, scores use
+// lane-groups over d with shuffle reductions (conflict-free shared reads), the softmax and the
+// a.v product run out of shared memory.
 // HBM-bound: L*d*4 bytes in per sample (x2 if v != k), d*4 out.
 #include "rtf_common.cuh"
 
@@ -57,12 +58,15 @@ __device__ __forceinline__ float act_bwd(int act, float z, float y) {
   }
 }
 
-// dot(vec[d], tile[l][d]) for every l, written to dst[l]; lane-groups of g lanes split d
+
+// dot(vec[d], tile[l][d]) for the rows l = first, first+step, ... of this warp; lane-groups of
+// g lanes split d (conflict-free shared reads), shuffle reduction inside the group
 __device__ __forceinline__ void rows_dot(const float* __restrict__ vec, const float* __restrict__ tile,
-                                         int L, int d, int g, int lane, float* __restrict__ dst) {
-  const int rpi = 32 / g;  // rows per iteration
+                                         int L, int d, int g, int lane, int warp, int nwarps,
+                                         float* __restrict__ dst) {
+  const int rpi = 32 / g;  // rows per warp iteration
   const int lg = lane % g, lr = lane / g;
-  for (int l0 = 0; l0 < L; l0 += rpi) {
+  for (int l0 = warp * rpi; l0 < L; l0 += nwarps * rpi) {
     const int l = l0 + lr;
     float acc = 0.f;
     if (l < L)
@@ -79,83 +83,99 @@ __device__ __forceinline__ void rows_dot(const float* __restrict__ vec, const fl
   }
 }
 
-template <bool BWD>
-__global__ void __launch_bounds__(256) din_kernel(const __grid_constant__ DinParams P, int warp_floats,
-                                                  int kv_same) {
+// One CTA (DIN_WARPS warps) per sample, persistent over samples.  The (L,d) key tile (and value
+// tile when distinct) arrives by one TMA bulk copy per tile on the CTA's mbarrier; rows are split
+// across warps for the score / dz / output passes, per-warp partial d-vectors are combined in
+// warp order (deterministic).
+template <bool BWD, int DIN_WARPS>
+__global__ void __launch_bounds__(DIN_WARPS * 32) din_kernel(const __grid_constant__ DinParams P,
+                                                             int kv_same) {
   extern __shared__ __align__(16) float smem[];
-  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int L = P.L, d = P.d;
   const int Lp = (L + 3) & ~3;
-  float* kt = smem + (size_t)warp * warp_floats;        // [L][d]
-  float* vt = kv_same ? kt : kt + L * d;                // [L][d]
-  float* u = (kv_same ? kt + L * d : vt + L * d);       // [d]   u, later reused
-  float* qs = u + d;                                    // [d]   q
-  float* zb = qs + d;                                   // [Lp]  pre-activation z
-  float* ab = zb + Lp;                                  // [Lp]  scores -> attention weights
+  // one tile stage per CTA: more resident CTAs per SM beat double buffering here (measured:
+  // the per-sample reduction, not the tile latency, is what limits a CTA)
+  const int stage_floats = (kv_same ? 1 : 2) * L * d;
+  float* u = smem + stage_floats;                       // [d]
+  float* qs = u + d;                                    // [d]
+  float* gs = qs + d;                                   // [d]   (bwd) gout
+  float* part = gs + d;                                 // [DIN_WARPS][d] per-warp partial vectors
+  float* zb = part + DIN_WARPS * d;                     // [Lp]  pre-activation z
+  float* ab = zb + Lp;                                  // [Lp]  attention weights
   float* db = ab + Lp;                                  // [Lp]  (bwd) da -> dz
-  uint64_t* bar = reinterpret_cast<uint64_t*>(db + Lp);
-  if (lane == 0) {
-    mbar_init(bar, 1);
+  uint64_t* bars = reinterpret_cast<uint64_t*>(db + Lp);  // [2]
+  if (threadIdx.x == 0) {
+    mbar_init(&bars[0], 1);
+    mbar_init(&bars[1], 1);
     mbar_fence_init();
   }
-  __syncwarp();
+  __syncthreads();
   int g = 1;
   while (g * 4 < d && g < 32) g <<= 1;
   const unsigned tile_bytes = (unsigned)L * d * 4u;
-  const long long stride = (long long)gridDim.x * nwarps;
-  long long b = (long long)blockIdx.x * nwarps + warp;
-  uint32_t parity = 0;
-  auto issue = [&](long long bb) {
-    if (lane == 0) {
-      mbar_expect_tx(bar, kv_same ? tile_bytes : 2 * tile_bytes);
-      bulk_g2s(kt, P.k + bb * P.k_sb, tile_bytes, bar);
-      if (!kv_same) bulk_g2s(vt, P.v + bb * P.v_sb, tile_bytes, bar);
+  uint32_t parity[2] = {0, 0};
+  auto issue = [&](long long bb, int st) {
+    if (threadIdx.x == 0) {
+      float* kd = smem;
+      mbar_expect_tx(&bars[st], kv_same ? tile_bytes : 2 * tile_bytes);
+      bulk_g2s(kd, P.k + bb * P.k_sb, tile_bytes, &bars[st]);
+      if (!kv_same) bulk_g2s(kd + L * d, P.v + bb * P.v_sb, tile_bytes, &bars[st]);
     }
   };
-  if (b < P.B) issue(b);
-  for (; b < P.B; b += stride) {
-    // u = (W2 - W3) + W4*q ; c = (W1 + W3).q + bias
+  long long b = blockIdx.x;
+  if (b < P.B) issue(b, 0);
+  for (; b < P.B; b += gridDim.x) {
+    const int st = 0;
+    const float* kt = smem;
+    const float* vt = kv_same ? kt : kt + L * d;
+    // u = (W2 - W3) + W4*q ; c = (W1 + W3).q + bias   (every warp computes c; warp 0 stores u, q)
     float cpart = 0.f;
     for (int c = lane; c < d; c += 32) {
       const float qv = P.q[b * P.q_sb + c];
       const float w1 = __ldg(P.W + c), w2 = __ldg(P.W + d + c), w3 = __ldg(P.W + 2 * d + c),
                   w4 = __ldg(P.W + 3 * d + c);
-      qs[c] = qv;
-      u[c] = (w2 - w3) + w4 * qv;
+      if (warp == 0) {
+        qs[c] = qv;
+        u[c] = (w2 - w3) + w4 * qv;
+        if (BWD) gs[c] = P.gout[b * P.go_sb + c];
+      }
       cpart = fmaf(w1 + w3, qv, cpart);
     }
     const float cc = warp_sum(cpart) + __ldg(P.bias);
-    __syncwarp();
-    mbar_wait(bar, parity);
-    parity ^= 1;
-    rows_dot(u, kt, L, d, g, lane, zb);
-    __syncwarp();
-    // activation, mask, softmax
+    __syncthreads();
+    mbar_wait(&bars[st], parity[st]);
+    parity[st] ^= 1;
+    rows_dot(u, kt, L, d, g, lane, warp, DIN_WARPS, zb);
+    __syncthreads();
+    // activation + mask + softmax statistics: every warp scans all L (L is small), each warp
+    // then writes the weights of its own strided rows
     float m = -INFINITY;
     for (int l = lane; l < L; l += 32) {
-      const float z = zb[l] + cc;
-      zb[l] = z;
-      float s = act_fwd(P.act, z);
+      const float s = act_fwd(P.act, zb[l] + cc);
       const bool keep = P.mask && P.mask[b * P.m_sb + l] != 0.f;
-      s = keep ? s : kPadLogit;
-      ab[l] = s;
-      m = fmaxf(m, s);
+      m = fmaxf(m, keep ? s : kPadLogit);
     }
     m = warp_max(m);
     float sum = 0.f;
     for (int l = lane; l < L; l += 32) {
-      const float e = expf(ab[l] - m);
-      ab[l] = e;
-      sum += e;
+      const float s = act_fwd(P.act, zb[l] + cc);
+      const bool keep = P.mask && P.mask[b * P.m_sb + l] != 0.f;
+      sum += expf((keep ? s : kPadLogit) - m);
     }
     sum = warp_sum(sum);
     const float inv = 1.f / sum;
-    for (int l = lane; l < L; l += 32) ab[l] *= inv;
-    __syncwarp();
+    for (int l = warp * 32 + lane; l < L; l += DIN_WARPS * 32) {
+      const float s = act_fwd(P.act, zb[l] + cc);
+      const bool keep = P.mask && P.mask[b * P.m_sb + l] != 0.f;
+      ab[l] = expf((keep ? s : kPadLogit) - m) * inv;
+    }
+    __syncthreads();
     if (!BWD) {
+      // out = a @ v : rows split across warps, partial vectors combined in warp order
       for (int c = lane * 4; c < d; c += 128) {
         float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
-        for (int l = 0; l < L; ++l) {
+        for (int l = warp; l < L; l += DIN_WARPS) {
           const float a = ab[l];
           const float4 vv = *reinterpret_cast<const float4*>(vt + (long long)l * d + c);
           acc.x = fmaf(a, vv.x, acc.x);
@@ -163,41 +183,47 @@ __global__ void __launch_bounds__(256) din_kernel(const __grid_constant__ DinPar
           acc.z = fmaf(a, vv.z, acc.z);
           acc.w = fmaf(a, vv.w, acc.w);
         }
-        float* o = P.out + b * P.o_sb + c;
-        o[0] = acc.x; o[1] = acc.y; o[2] = acc.z; o[3] = acc.w;
+        *reinterpret_cast<float4*>(part + warp * d + c) = acc;
+      }
+      __syncthreads();
+      for (int c = threadIdx.x; c < d; c += DIN_WARPS * 32) {
+        float acc = 0.f;
+#pragma unroll
+        for (int w = 0; w < DIN_WARPS; ++w) acc += part[w * d + c];
+        P.out[b * P.o_sb + c] = acc;
       }
     } else {
-      // da_l = gout . v_l  (gout staged over q's slot is not possible: q is needed) -> use u? no:
-      // keep u; stage gout in registers per lane-group via a small shared vector reuse of db? db is
-      // [Lp] floats; gout needs d floats -> stage it after db (room reserved by warp_floats).
-      float* gs = reinterpret_cast<float*>(bar + 2);  // [d] gout staging (16-byte aligned)
-      for (int c = lane; c < d; c += 32) gs[c] = P.gout[b * P.go_sb + c];
-      __syncwarp();
-      rows_dot(gs, vt, L, d, g, lane, db);
-      __syncwarp();
+      rows_dot(gs, vt, L, d, g, lane, warp, DIN_WARPS, db);  // da_l = gout . v_l
+      __syncthreads();
       float dotp = 0.f;
       for (int l = lane; l < L; l += 32) dotp = fmaf(ab[l], db[l], dotp);
       dotp = warp_sum(dotp);
+      // dz for all l (every warp, for dc); each warp stores only its rows afterwards
       float dcp = 0.f;
       for (int l = lane; l < L; l += 32) {
         const bool keep = P.mask && P.mask[b * P.m_sb + l] != 0.f;
-        const float z = zb[l];
+        const float z = zb[l] + cc;
         const float y = act_fwd(P.act, z);
-        const float ds = keep ? ab[l] * (db[l] - dotp) : 0.f;  // padded score is a constant
-        const float dz = ds * act_bwd(P.act, z, y);
-        db[l] = dz;
-        dcp += dz;
+        const float ds = keep ? ab[l] * (db[l] - dotp) : 0.f;  // a padded score is a constant
+        dcp += ds * act_bwd(P.act, z, y);
       }
       const float dc = warp_sum(dcp);
-      __syncwarp();
+      __syncthreads();  // everyone has read db (= da) before it is overwritten with dz
+      for (int l = warp * 32 + lane; l < L; l += DIN_WARPS * 32) {
+        const bool keep = P.mask && P.mask[b * P.m_sb + l] != 0.f;
+        const float z = zb[l] + cc;
+        const float y = act_fwd(P.act, z);
+        const float da = db[l];
+        db[l] = (keep ? ab[l] * (da - dotp) : 0.f) * act_bwd(P.act, z, y);
+      }
+      __syncthreads();
       float* gk = P.gk + b * P.gk_sb;
       float* gv = P.gv + b * P.gv_sb;
-      float* gw = P.gw_rows + b * (4LL * d + 1);
       for (int c = lane * 4; c < d; c += 128) {
         float4 du = make_float4(0.f, 0.f, 0.f, 0.f);
         const float4 uu = *reinterpret_cast<const float4*>(u + c);
         const float4 gg = *reinterpret_cast<const float4*>(gs + c);
-        for (int l = 0; l < L; ++l) {
+        for (int l = warp; l < L; l += DIN_WARPS) {
           const float dz = db[l], a = ab[l];
           const float4 kk = *reinterpret_cast<const float4*>(kt + (long long)l * d + c);
           du.x = fmaf(dz, kk.x, du.x);
@@ -209,47 +235,55 @@ __global__ void __launch_bounds__(256) din_kernel(const __grid_constant__ DinPar
           *reinterpret_cast<float4*>(gv + (long long)l * d + c) =
               make_float4(a * gg.x, a * gg.y, a * gg.z, a * gg.w);
         }
-        const float duv[4] = {du.x, du.y, du.z, du.w};
-#pragma unroll
-        for (int e = 0; e < 4; ++e) {
-          const int ci = c + e;
-          const float qv = qs[ci];
-          const float w1 = __ldg(P.W + ci), w3 = __ldg(P.W + 2 * d + ci), w4 = __ldg(P.W + 3 * d + ci);
-          P.gq[b * P.gq_sb + ci] = dc * (w1 + w3) + duv[e] * w4;
-          gw[ci] = dc * qv;
-          gw[d + ci] = duv[e];
-          gw[2 * d + ci] = dc * qv - duv[e];
-          gw[3 * d + ci] = duv[e] * qv;
-        }
+        *reinterpret_cast<float4*>(part + warp * d + c) = du;
       }
-      if (lane == 0) gw[4 * d] = dc;
+      __syncthreads();
+      float* gw = P.gw_rows + b * (4LL * d + 1);
+      for (int ci = threadIdx.x; ci < d; ci += DIN_WARPS * 32) {
+        float duv = 0.f;
+#pragma unroll
+        for (int w = 0; w < DIN_WARPS; ++w) duv += part[w * d + ci];
+        const float qv = qs[ci];
+        const float w1 = __ldg(P.W + ci), w3 = __ldg(P.W + 2 * d + ci), w4 = __ldg(P.W + 3 * d + ci);
+        P.gq[b * P.gq_sb + ci] = dc * (w1 + w3) + duv * w4;
+        gw[ci] = dc * qv;
+        gw[d + ci] = duv;
+        gw[2 * d + ci] = dc * qv - duv;
+        gw[3 * d + ci] = duv * qv;
+      }
+      if (threadIdx.x == 0) gw[4 * d] = dc;
     }
-    __syncwarp();
-    if (b + stride < P.B) issue(b + stride);
+    __syncthreads();  // all reads of the tiles / the scratch vectors are done
+    if (b + gridDim.x < P.B) issue(b + gridDim.x, 0);
   }
 }
 
-static int din_launch(const DinParams& P, bool bwd, cudaStream_t st) {
+template <int NW>
+static int din_launch_nw(const DinParams& P, bool bwd, int kv_same, cudaStream_t st) {
   const int L = P.L, d = P.d, Lp = (L + 3) & ~3;
-  const int kv_same = (P.k == P.v && P.k_sb == P.v_sb) ? 1 : 0;
-  // tiles + u + q + z/a/d + mbarrier slot (4 floats) + gout staging (d)
-  const int warp_floats = (kv_same ? 1 : 2) * L * d + 2 * d + 3 * Lp + 4 + d;
-  const size_t per_warp = (size_t)warp_floats * 4;
-  int nwarps = (int)((227 * 1024) / per_warp);
-  if (nwarps < 1) return RTF_E_RANGE;
-  if (nwarps > 8) nwarps = 8;
-  const size_t smem = per_warp * nwarps;
-  auto kern = bwd ? din_kernel<true> : din_kernel<false>;
+  const size_t floats = (size_t)(kv_same ? 1 : 2) * L * d + 3 * (size_t)d + (size_t)NW * d +
+                        3 * (size_t)Lp + 4;
+  const size_t smem = floats * 4;
+  if (smem > 227 * 1024) return RTF_E_RANGE;
+  auto kern = bwd ? din_kernel<true, NW> : din_kernel<false, NW>;
   cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   if (e != cudaSuccess) return (int)e;
-  int per_sm = (int)((227 * 1024) / smem);
+  int per_sm = (int)((227 * 1024) / (smem + 1024));
   if (per_sm < 1) per_sm = 1;
-  if (per_sm > 4) per_sm = 4;
-  long long blocks = (P.B + nwarps - 1) / nwarps;
+  if (per_sm > 64 / NW) per_sm = 64 / NW;
+  if (per_sm > 16) per_sm = 16;
+  long long blocks = P.B;
   if (blocks > (long long)kNumSMs * per_sm) blocks = (long long)kNumSMs * per_sm;
-  kern<<<(unsigned)blocks, nwarps * 32, smem, st>>>(P, warp_floats, kv_same);
+  kern<<<(unsigned)blocks, NW * 32, smem, st>>>(P, kv_same);
   RTF_CHECK_LAUNCH();
   return 0;
+}
+
+static int din_launch(const DinParams& P, bool bwd, cudaStream_t st) {
+  const int kv_same = (P.k == P.v && P.k_sb == P.v_sb) ? 1 : 0;
+  // small tiles: one warp per sample (more samples in flight); large tiles: 8 warps cooperate
+  if ((long long)P.L * P.d <= 4096) return din_launch_nw<1>(P, bwd, kv_same, st);
+  return din_launch_nw<8>(P, bwd, kv_same, st);
 }
 
 static int din_check(int64_t B, int L, int d, int act, const float* q, const float* k,
