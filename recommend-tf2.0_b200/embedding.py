@@ -281,7 +281,8 @@ class EmbeddingTables(torch.nn.Module):
         for t, w in enumerate(self.weights):
             sel = tab == t
             grads.append(torch.sparse_coo_tensor(row[sel].unsqueeze(0), g[sel][:, : w.shape[1]],
-                                                 size=w.shape, check_invariants=False).coalesce())
+                                                 size=w.shape, check_invariants=False,
+                                                 is_coalesced=True))   # keys are unique and sorted
         return tuple(grads)
 
     def check_ids(self):
