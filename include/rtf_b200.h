@@ -266,6 +266,15 @@ int rtf_sampled_softmax_bwd(const float* d_x, int64_t x_sb, const float* d_W, co
                             const float* d_gloss, float* d_gx, int64_t gx_sb, float* d_G,
                             void* d_ws, void* stream);
 
+/* ---- dense-layer backward epilogue (MLP either side of the path) ------------
+ * replaces: ReluGrad + BiasAddGrad after the Dense layers of ctr.layers.modules.DNN
+ *           (src/ctr/layers/modules.py:129-135) — two passes over the (B,N) gradient become one.
+ * d_g = d_gy * (d_y > 0)  (d_y NULL: no mask, d_g untouched) and d_colsum[c] = sum_b d_g[b,c]
+ * in the deterministic 2-stage order of rtf_colsum.  Contiguous (B, cols), cols % 4 == 0.     */
+int rtf_relu_bwd_colsum_workspace(int64_t B, int cols, size_t* bytes);
+int rtf_relu_bwd_colsum(const float* d_gy, const float* d_y, int64_t B, int cols, float* d_g,
+                        float* d_colsum, void* d_ws, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

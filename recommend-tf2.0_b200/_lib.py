@@ -57,6 +57,8 @@ SIGNATURES = {
                           _p, _i64, _p, _i64, _p],
     "rtf_colsum_workspace": [_i64, _int, C.POINTER(C.c_size_t)],
     "rtf_colsum": [_p, _i64, _p, _i64, _int, _p, _p, _p],
+    "rtf_relu_bwd_colsum_workspace": [_i64, _int, C.POINTER(C.c_size_t)],
+    "rtf_relu_bwd_colsum": [_p, _p, _i64, _int, _p, _p, _p, _p],
     "rtf_fm_layer_workspace": [_i64, _int, C.POINTER(C.c_size_t)],
     "rtf_fm_layer_fwd": [_p, _i64, _p, _int, _p, _i64, _int, _int, _i64, _int, _int, _p, _p, _p],
     "rtf_fm_layer_bwd": [_p, _i64, _p, _int, _p, _i64, _int, _int, _i64, _int, _int, _p, _p,

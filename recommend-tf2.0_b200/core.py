@@ -156,6 +156,27 @@ def _wgrad(x: torch.Tensor, g: torch.Tensor) -> torch.Tensor:
     return x.t() @ g
 
 
+def _relu_bwd_bias_grad(gy: torch.Tensor, y):
+    """(g, db): g = gy * (y > 0) (g is gy itself when y is None) and db = g.sum(0), in one pass
+    through librtf_b200 (rtf_relu_bwd_colsum) when the layout allows, else framework ops."""
+    B, N = gy.shape
+    if gy.is_cuda and N % 4 == 0 and B > 0:
+        import ctypes as C
+        from . import _lib as L
+        gy = gy.contiguous()
+        nb = C.c_size_t(0)
+        L.check(L.lib().rtf_relu_bwd_colsum_workspace(B, N, C.byref(nb)), "rtf_relu_bwd_colsum_workspace")
+        ws = torch.empty(nb.value, dtype=torch.uint8, device=gy.device)
+        g = torch.empty_like(gy) if y is not None else gy
+        db = torch.empty(N, dtype=torch.float32, device=gy.device)
+        L.check(L.lib().rtf_relu_bwd_colsum(gy.data_ptr(), None if y is None else y.data_ptr(), B, N,
+                                            g.data_ptr(), db.data_ptr(), ws.data_ptr(),
+                                            L.current_stream_ptr()), "rtf_relu_bwd_colsum")
+        return g, db
+    g = torch.ops.aten.threshold_backward(gy, y, 0.0) if y is not None else gy.contiguous()
+    return g, g.sum(0)
+
+
 class _DenseFn(torch.autograd.Function):
     """x W + b (optionally ReLU) with bias / ReLU in the library GEMM's epilogue — one pass over
     the output instead of three; backward masks the incoming gradient once, split-K weight grad."""
@@ -170,10 +191,9 @@ class _DenseFn(torch.autograd.Function):
     @staticmethod
     def backward(ctx, gy):
         x, w, y = ctx.saved_tensors
-        g = torch.ops.aten.threshold_backward(gy, y, 0.0) if ctx.relu else gy.contiguous()
+        g, gb = _relu_bwd_bias_grad(gy, y if ctx.relu else None)
         gx = g @ w.t() if ctx.needs_input_grad[0] else None
         gw = _wgrad(x, g) if ctx.needs_input_grad[1] else None
-        gb = g.sum(0) if ctx.needs_input_grad[2] else None
         return gx, gw, gb, None
 
 

@@ -1,0 +1,76 @@
+// Dense-layer backward epilogue (the MLP either side of the hot path).
+//
+// The GEMMs of the dense layers are library calls; what the framework adds around them in the
+// backward is two more passes over the (B, N) gradient: the ReLU mask (threshold_backward) and
+// the bias gradient (a column sum).  This kernel does both in ONE pass: g = gy * (y > 0) is
+// written once and its column sums are accumulated on the fly, with the same deterministic
+// two-stage order as rtf_colsum (256-row chunks, chunks combined in order).
+#include "rtf_common.cuh"
+
+namespace rtf {
+
+constexpr int RB_ROWS = 128;
+
+__global__ void __launch_bounds__(128)
+relu_bwd_colsum_stage1(const float* __restrict__ gy, const float* __restrict__ y, long long B,
+                       int Ccols, float* __restrict__ g, float* __restrict__ partial) {
+  const int c4 = (blockIdx.x * blockDim.x + threadIdx.x) * 4;
+  if (c4 >= Ccols) return;
+  const long long b0 = (long long)blockIdx.y * RB_ROWS;
+  const long long b1 = min(b0 + RB_ROWS, B);
+  float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+  for (long long b = b0; b < b1; ++b) {
+    const float4 gv = *reinterpret_cast<const float4*>(gy + b * Ccols + c4);
+    float4 o = gv;
+    if (y) {
+      const float4 yv = *reinterpret_cast<const float4*>(y + b * Ccols + c4);
+      o.x = yv.x > 0.f ? gv.x : 0.f;
+      o.y = yv.y > 0.f ? gv.y : 0.f;
+      o.z = yv.z > 0.f ? gv.z : 0.f;
+      o.w = yv.w > 0.f ? gv.w : 0.f;
+      *reinterpret_cast<float4*>(g + b * Ccols + c4) = o;
+    }
+    acc = f4_add(acc, o);
+  }
+  *reinterpret_cast<float4*>(partial + (long long)blockIdx.y * Ccols + c4) = acc;
+}
+
+__global__ void __launch_bounds__(128)
+relu_bwd_colsum_stage2(const float* __restrict__ partial, int nchunks, int Ccols,
+                       float* __restrict__ out) {
+  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= Ccols) return;
+  float acc = 0.f;
+  for (int k = 0; k < nchunks; ++k) acc = __fadd_rn(acc, partial[(long long)k * Ccols + c]);
+  out[c] = acc;
+}
+
+}  // namespace rtf
+
+using namespace rtf;
+
+extern "C" int rtf_relu_bwd_colsum_workspace(int64_t B, int cols, size_t* bytes) {
+  if (!bytes || B < 0 || cols <= 0) return RTF_E_ARG;
+  *bytes = (size_t)((B + RB_ROWS - 1) / RB_ROWS + 1) * (size_t)cols * 4;
+  return 0;
+}
+
+// d_g = d_gy * (d_y > 0) (skipped when d_y is NULL: then only the column sums of d_gy are taken)
+// d_colsum[c] = sum_b d_g[b, c].  Contiguous (B, cols) row-major, cols % 4 == 0, 16-byte aligned.
+extern "C" int rtf_relu_bwd_colsum(const float* d_gy, const float* d_y, int64_t B, int cols,
+                                   float* d_g, float* d_colsum, void* d_ws, void* stream) {
+  if (B < 0 || cols <= 0 || !d_colsum) return RTF_E_ARG;
+  cudaStream_t st = (cudaStream_t)stream;
+  if (B == 0) return (int)cudaMemsetAsync(d_colsum, 0, (size_t)cols * 4, st);
+  if (!d_gy || !d_ws || (d_y && !d_g)) return RTF_E_ARG;
+  if (cols % 4 || (uintptr_t)d_gy % 16 || (uintptr_t)d_y % 16 || (uintptr_t)d_g % 16 ||
+      (uintptr_t)d_ws % 16)
+    return RTF_E_ALIGN;
+  const int nchunks = (int)((B + RB_ROWS - 1) / RB_ROWS);
+  dim3 g1((cols / 4 + 127) / 128, nchunks);
+  relu_bwd_colsum_stage1<<<g1, 128, 0, st>>>(d_gy, d_y, B, cols, d_g, (float*)d_ws);
+  relu_bwd_colsum_stage2<<<(cols + 127) / 128, 128, 0, st>>>((const float*)d_ws, nchunks, cols,
+                                                             d_colsum);
+  RTF_CHECK_LAUNCH();
+  return 0;
+}
