@@ -45,7 +45,7 @@ def parse_args():
     ap.add_argument("--mlp-gemm", default="bf16x9", choices=["bf16x9", "native"],
                     help="dense-MLP GEMMs: cuBLAS 12.9 FP32 emulation (BF16x9, fp32-accurate) or SGEMM")
     ap.add_argument("--pad-to", type=int, default=8, help="round the interaction width up (479 -> 480)")
-    ap.add_argument("--exchange", default="nccl", choices=["p2p", "nccl"],
+    ap.add_argument("--exchange", default="p2p", choices=["p2p", "nccl"],
                     help="multi-GPU row exchange: fused into K4 over NVLink peer memory, or NCCL all-to-all")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-kernel-timing", action="store_true")

@@ -129,9 +129,12 @@ int rtf_dot_interact_bwd(const float* d_x, const float* d_gout, int64_t gout_sb,
  * row_base[i] + b*row_stride[i] (HOST arrays of F1 device pointers / element strides).  Used
  * by the multi-GPU path to interact straight out of the all-to-all receive buffer (blocks
  * ordered by source rank) and to write dX rows into the send buffer of the backward
- * exchange, with no permute copy.                                            */
+ * exchange, with no permute copy.
+ * d_xsave (optional, (B, (F1-1)*D) with sample stride xsave_sb): rows 1..F1-1 as staged, so the
+ * backward can re-read them locally when the forward pulled them from peers over NVLink.   */
 int rtf_dot_rows_fwd(const float* const* row_base, const int64_t* row_stride, int F1, int D,
-                     int64_t B, float* d_out, int64_t out_sb, int out_cols, void* stream);
+                     int64_t B, float* d_out, int64_t out_sb, int out_cols, float* d_xsave,
+                     int64_t xsave_sb, void* stream);
 int rtf_dot_rows_bwd(const float* const* row_base, const int64_t* row_stride, int F1, int D,
                      int64_t B, const float* d_gout, int64_t gout_sb, float* const* grad_base,
                      const int64_t* grad_stride, void* stream);

@@ -49,7 +49,7 @@ SIGNATURES = {
                             C.POINTER(rtf_opt), _p, _p, _p, C.c_size_t, _p],
     "rtf_dot_interact_fwd": [_p, _i64, _int, _int, _p, _i64, _int, _p],
     "rtf_dot_interact_bwd": [_p, _p, _i64, _i64, _int, _int, _p, _p],
-    "rtf_dot_rows_fwd": [_p, _p, _int, _int, _i64, _p, _i64, _int, _p],
+    "rtf_dot_rows_fwd": [_p, _p, _int, _int, _i64, _p, _i64, _int, _p, _i64, _p],
     "rtf_dot_rows_bwd": [_p, _p, _int, _int, _i64, _p, _i64, _p, _p, _p],
     "rtf_embed_dot_fwd": [_p, _p, _int, _int, _p, _int, _i64, _i64, _i64, _p, _i64, _p, _i64,
                           _int, _p, _p],

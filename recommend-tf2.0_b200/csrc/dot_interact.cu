@@ -35,6 +35,8 @@ struct DotParams {
   long long out_sb;
   const float* gout;  // bwd
   long long gout_sb;
+  float* xsave;  // fwd, optional: rows 1..F1-1 of every sample copied to (B, (F1-1)*D) — lets a
+  long long xsave_sb;  // backward re-read rows locally when the forward pulled them over NVLink
   int32_t* err;
 };
 
@@ -155,6 +157,15 @@ dot_fwd_kernel(const __grid_constant__ DotParams P, int warp_floats) {
     for (int d = lane; d < D; d += 32) o[d] = xt[d];
     for (int p = lane; p < npairs; p += 32) o[D + p] = zst[p];
     for (int p = D + npairs + lane; p < P.out_cols; p += 32) o[p] = 0.f;
+    if (P.xsave) {
+      float* xs = P.xsave + b * P.xsave_sb;
+      const int nv = D >> 2;
+      for (int e = lane; e < (F1 - 1) * nv; e += 32) {
+        const int r = e / nv, c = e - r * nv;
+        *reinterpret_cast<float4*>(xs + r * D + 4 * c) =
+            *reinterpret_cast<const float4*>(xt + (r + 1) * RS + 4 * c);
+      }
+    }
     __syncwarp();  // every lane is done reading xt/zst before the next sample overwrites them
     if (b + stride < P.B) dot_issue_rows<IdT>(P, b + stride, xt, RS, bar, lane);
   }
@@ -510,7 +521,7 @@ static int dot_launch(Kern kern, const DotParams& P, int warp_floats, int cta_fl
 static int dot_fwd_impl(DotParams& P, int ids_i64, cudaStream_t st) {
   const int F1p = (P.F1 + 3) & ~3, RS = dot_row_stride(P.D);
   const int npairs = P.F1 * (P.F1 - 1) / 2;
-  if (dot_use_mma(P.F1, P.D)) {
+  if (dot_use_mma(P.F1, P.D) && !P.xsave) {
     const int wf = 32 * RS + ((npairs + 3) & ~3) + 4;
     return ids_i64 ? dot_launch(dot_fwd_mma_kernel<int64_t>, P, wf, 0, st)
                    : dot_launch(dot_fwd_mma_kernel<int32_t>, P, wf, 0, st);
@@ -592,7 +603,7 @@ extern "C" int rtf_dot_interact_bwd(const float* d_x, const float* d_gout, int64
 // the all-to-all receive buffer (source-major blocks) without a permute copy.
 extern "C" int rtf_dot_rows_fwd(const float* const* row_base, const int64_t* row_stride, int F1,
                                 int D, int64_t B, float* d_out, int64_t out_sb, int out_cols,
-                                void* stream) {
+                                float* d_xsave, int64_t xsave_sb, void* stream) {
   int rc = dot_check_common(B, F1, D);
   if (rc) return rc;
   if (B == 0) return 0;
@@ -606,6 +617,9 @@ extern "C" int rtf_dot_rows_fwd(const float* const* row_base, const int64_t* row
     P.rbase[i] = row_base[i];
     P.rstride[i] = row_stride[i];
   }
+  if (d_xsave && ((uintptr_t)d_xsave % 16 || xsave_sb % 4 || xsave_sb < (int64_t)(F1 - 1) * D))
+    return RTF_E_ALIGN;
+  P.xsave = d_xsave; P.xsave_sb = xsave_sb;
   P.B = B; P.F1 = F1; P.D = D; P.out = d_out; P.out_sb = out_sb; P.out_cols = out_cols;
   return dot_fwd_impl(P, 0, (cudaStream_t)stream);
 }

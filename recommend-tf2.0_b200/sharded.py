@@ -136,7 +136,7 @@ class _ShardedInteractFn(torch.autograd.Function):
         cols = dot_out_cols(F1, D, pad_to)
         out = torch.empty((B, cols), dtype=torch.float32, device=dense.device)
         rb, rs = _row_tables(lay, recv, dense, B, D)
-        L.check(L.lib().rtf_dot_rows_fwd(rb, rs, F1, D, B, out.data_ptr(), cols, cols,
+        L.check(L.lib().rtf_dot_rows_fwd(rb, rs, F1, D, B, out.data_ptr(), cols, cols, None, 0,
                                          L.current_stream_ptr()), "rtf_dot_rows_fwd")
         ctx.model = model
         ctx.save_for_backward(dense, recv)
@@ -191,22 +191,28 @@ class _PeerInteractFn(torch.autograd.Function):
         cols = dot_out_cols(F1, D, pad_to)
         out = torch.empty((B, cols), dtype=torch.float32, device=dense.device)
         rb, rs = _peer_row_tables(lay, model._out_hdl.buffer_ptrs, dense, B, D)
+        xsave = torch.empty((B, (F1 - 1) * D), dtype=torch.float32, device=dense.device)
         L.check(L.lib().rtf_dot_rows_fwd(rb, rs, F1, D, B, out.data_ptr(), cols, cols,
+                                         xsave.data_ptr(), xsave.stride(0),
                                          L.current_stream_ptr()), "rtf_dot_rows_fwd")
         ctx.model = model
-        ctx.save_for_backward(dense)
+        ctx.save_for_backward(dense, xsave)
         return out
 
     @staticmethod
     def backward(ctx, gout):
-        (dense,) = ctx.saved_tensors
+        dense, xsave = ctx.saved_tensors
         model = ctx.model
         lay = model.layout
         gout = gout.contiguous()
         B, D = dense.shape
         F1 = lay.n_tables + 1
         gdense = torch.empty_like(dense)
-        rb, rs = _peer_row_tables(lay, model._out_hdl.buffer_ptrs, dense, B, D)
+        # rows come back from the local copy the forward kept (no second trip over NVLink) ...
+        base = [dense.data_ptr()] + [xsave.data_ptr() + t * D * 4 for t in range(F1 - 1)]
+        stride = [dense.stride(0)] + [xsave.stride(0)] * (F1 - 1)
+        rb, rs = (C.c_void_p * F1)(*base), (C.c_int64 * F1)(*stride)
+        # ... and the dX rows are stored straight into their owners' gradient buffers
         gb, gs = _peer_row_tables(lay, model._grad_hdl.buffer_ptrs, gdense, B, D)
         L.check(L.lib().rtf_dot_rows_bwd(rb, rs, F1, D, B, gout.data_ptr(), gout.stride(0), gb, gs,
                                          L.current_stream_ptr()), "rtf_dot_rows_bwd")
@@ -221,7 +227,7 @@ class ShardedDLRM(Layer):
                  top_dnn_hidden_units=(128, 64), activation="relu", dnn_dropout=0.0, embed_reg=1e-4,
                  sparse_optimizer: Optional[SparseOptimizer] = None, pad_to: int = 1,
                  input_bn: bool = True, seed: Optional[int] = None, owners=None,
-                 exchange: str = "nccl"):
+                 exchange: str = "p2p"):
         super().__init__()
         if exchange not in ("p2p", "nccl"):
             raise ValueError(exchange)
@@ -257,6 +263,13 @@ class ShardedDLRM(Layer):
         ids_global = exchange_ids(sparse_inputs, self.world)                       # (B_global, F)
         local_ids = ids_global.index_select(1, self._mine_idx).contiguous()        # (B_global, T_me)
         self._saved = local_ids
+        if self.exchange == "p2p":
+            try:
+                self._ensure_symmetric(B_local)
+            except Exception as e:  # no peer access on this box: use the NCCL all-to-all instead
+                import warnings
+                warnings.warn(f"symmetric memory unavailable ({e}); row exchange falls back to NCCL")
+                self.exchange = "nccl"
         if self.exchange == "p2p":
             return self._call_p2p(dense_inputs, local_ids, B_local)
         with torch.no_grad():
