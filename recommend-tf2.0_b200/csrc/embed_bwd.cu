@@ -13,6 +13,8 @@
 //      are combined in chunk order — the summation tree depends only on the segment, so
 //      results are reproducible bit for bit — then the optimizer updates the row in place.
 // HBM-bound: per lookup one gradient row read, per touched row W/m/v read+write.
+#include <cstdlib>
+
 #include "rtf_common.cuh"
 
 namespace rtf {
@@ -460,9 +462,14 @@ struct SegWork {
   int dim_max;
 };
 
-// A: one lane-group per segment; short segments are finished here
+// A: one lane-group per segment; short segments are finished here.
+// Tuning record (B200, DLRM cfg, ncu gpu__time_duration): the kernel is bound by a chain of
+// dependent memory round trips (seg_start -> key/vals -> gradient rows -> W/m/v), so resident
+// warps matter most: capping registers at 32 (64 warps/SM, ~90 B of spill) gives 511 us vs
+// 556 us at 48 registers; loading W/m/v before the gradient sum was slower at every register
+// cap tried (566-620 us), a persistent grid-stride variant 587 us.
 template <int VEC, int G, int VPL>
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(256, 8)
 seg_short(const __grid_constant__ BwdParams P, const __grid_constant__ SegWork S,
           const float* __restrict__ grad) {
   const long long gid = ((long long)blockIdx.x * blockDim.x + threadIdx.x) / G;
@@ -496,7 +503,6 @@ seg_short(const __grid_constant__ BwdParams P, const __grid_constant__ SegWork S
     for (int e = 0; e < VEC; ++e) acc[k].v[e] = 0.f;
   const float scale = __fdiv_rn(1.0f, (float)P.L);
   sum_rows<VEC, G, VPL>(P, grad, S.vals, start, end, nv, lg, scale, acc);
-  // (loading W/m/v before the gradient sum was measured 14 % slower: 12 more live registers)
   RowState<VEC, VPL> st;
   load_row_state<VEC, G, VPL>(P, key, nv, lg, st);
   finish_row<VEC, G, VPL>(P, key, seg, nv, lg, acc, st, S.uniq_key, S.uniq_grad, S.dim_max);
