@@ -469,7 +469,7 @@ struct SegWork {
 // 556 us at 48 registers; loading W/m/v before the gradient sum was slower at every register
 // cap tried (566-620 us), a persistent grid-stride variant 587 us.
 template <int VEC, int G, int VPL>
-__global__ void __launch_bounds__(256, 8)
+__global__ void __launch_bounds__(256, VPL == 1 ? 8 : 4)
 seg_short(const __grid_constant__ BwdParams P, const __grid_constant__ SegWork S,
           const float* __restrict__ grad) {
   const long long gid = ((long long)blockIdx.x * blockDim.x + threadIdx.x) / G;
