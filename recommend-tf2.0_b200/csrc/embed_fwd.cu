@@ -24,8 +24,11 @@ struct FwdFields {
   int sumD;                 // width of one full output row (all fields)
 };
 
+// Register cap: with one float4 per lane the kernel is pure latency hiding, so 32 registers
+// (64 resident warps/SM, ~60 B of spill) beat 40 and 64 registers: 240 vs 252 vs 290 us on the
+// DLRM configuration (ncu gpu__time_duration, profiles/README.md).
 template <typename IdT, int G, int VPL>
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(256, VPL == 1 ? 8 : 4)
 embed_fwd_vec(const __grid_constant__ FwdFields P, const IdT* __restrict__ ids, long long B,
               int L, long long sb, long long sf, long long sl, int pool,
               float* __restrict__ out, long long out_sb, int32_t* err) {
