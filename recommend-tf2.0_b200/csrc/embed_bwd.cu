@@ -510,7 +510,7 @@ seg_short(const __grid_constant__ BwdParams P, const __grid_constant__ SegWork S
 
 // B: one lane-group per chunk of a long segment -> partial sums
 template <int VEC, int G, int VPL>
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(256, VPL == 1 ? 8 : 4)
 seg_partial(const __grid_constant__ BwdParams P, const __grid_constant__ SegWork S,
             const float* __restrict__ grad) {
   const long long gid = ((long long)blockIdx.x * blockDim.x + threadIdx.x) / G;
@@ -538,7 +538,7 @@ seg_partial(const __grid_constant__ BwdParams P, const __grid_constant__ SegWork
 
 // C: one lane-group per long segment combines its chunk partials in chunk order
 template <int VEC, int G, int VPL>
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(256, VPL == 1 ? 8 : 4)
 seg_combine(const __grid_constant__ BwdParams P, const __grid_constant__ SegWork S) {
   const long long gid = ((long long)blockIdx.x * blockDim.x + threadIdx.x) / G;
   const int lg = (int)(threadIdx.x % G);
