@@ -45,8 +45,11 @@ def parse_args():
     ap.add_argument("--mlp-gemm", default="bf16x9", choices=["bf16x9", "native"],
                     help="dense-MLP GEMMs: cuBLAS 12.9 FP32 emulation (BF16x9, fp32-accurate) or SGEMM")
     ap.add_argument("--pad-to", type=int, default=8, help="round the interaction width up (479 -> 480)")
-    ap.add_argument("--exchange", default="p2p", choices=["p2p", "nccl"],
-                    help="multi-GPU row exchange: fused into K4 over NVLink peer memory, or NCCL all-to-all")
+    ap.add_argument("--exchange", default="peer", choices=["peer", "p2p", "nccl"],
+                    help="multi-GPU row exchange: 'peer' = tables sharded table-wise + row-wise, rows "
+                         "pulled / gradients pushed over NVLink inside K4; 'p2p' = table-wise, pooled rows "
+                         "pulled from the owners' K1 output; 'nccl' = table-wise, NCCL all-to-all")
+    ap.add_argument("--row-wise-min-rows", type=int, default=5_000_000)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-kernel-timing", action="store_true")
     return ap.parse_args()
@@ -146,7 +149,9 @@ def bench_config(args, world):
             "optimizer": "adam (sparse rows fused in K2, dense MLP torch fused)",
             "l2_flush": "inputs larger than L2: 17.2 GB of tables, distinct batch every step",
             "parallelism": "single" if world == 1 else
-            f"tables sharded over {world} GPUs ({args.exchange} row exchange) + dp MLP"}
+            f"tables sharded over {world} GPUs ({args.exchange} row exchange"
+            + (f", row-wise >= {args.row_wise_min_rows} rows" if args.exchange == "peer" else "")
+            + ") + dp MLP"}
 
 
 def run_reference(args):
@@ -303,8 +308,12 @@ def run_b200(args):
         model = pkg.DLRM(fc, BOT_MLP, TOP_MLP, interaction="dot", seed=1234, pad_to=args.pad_to)
         trainer = pkg.DLRMTrainer(model, lr=1e-3)
     else:
-        from recommend_tf2_b200.sharded import ShardedDLRM, ShardedDLRMTrainer
-        model = ShardedDLRM(fc, BOT_MLP, TOP_MLP, seed=1234, pad_to=args.pad_to, exchange=args.exchange)
+        from recommend_tf2_b200.sharded import PeerShardedDLRM, ShardedDLRM, ShardedDLRMTrainer
+        if args.exchange == "peer":
+            model = PeerShardedDLRM(fc, BOT_MLP, TOP_MLP, seed=1234, pad_to=args.pad_to,
+                                    row_wise_min_rows=args.row_wise_min_rows)
+        else:
+            model = ShardedDLRM(fc, BOT_MLP, TOP_MLP, seed=1234, pad_to=args.pad_to, exchange=args.exchange)
         trainer = ShardedDLRMTrainer(model, lr=1e-3)
 
     host = make_batches(W + K, B, CRITEO_ROWS, args.ids, seed=1000 + rank)
@@ -368,6 +377,9 @@ def run_b200(args):
             cpu = {k: cpu[k] for k in ("value", "unit", "cores", "kind", "sample")}
         if world == 1:   # fused gather+dot fwd, its bwd, K2 pipeline
             per_step = 2 + embed_bwd_launches(CRITEO_ROWS, len(CRITEO_ROWS))
+        elif args.exchange == "peer":   # per rank: fused gather+dot fwd/bwd + K2 over the rank's shards
+            mine = [model.layout.local_rows(0, t) for t in model.layout.fields[0]]
+            per_step = (2 + embed_bwd_launches(mine, len(mine))) * world
         else:            # per rank: K1 + dot-rows fwd/bwd + K2 over the rank's own tables
             mine = [CRITEO_ROWS[t] for t in model.layout.slots[0]]
             per_step = (3 + embed_bwd_launches(mine, len(mine))) * world

@@ -155,6 +155,27 @@ int rtf_embed_dot_bwd(const float* const* tables, const int64_t* rows, int n_fie
                       int64_t gout_sb, float* d_gdense, int64_t gdense_sb, float* d_gemb,
                       int64_t gemb_sb, void* stream);
 
+/* ---- K1+K4 over tables sharded across G GPUs (table-wise AND row-wise), NVLink peer memory ----
+ * The exchange of SURVEY §8e fused into the interaction kernel: every rank keeps its table
+ * shards in peer-mapped memory; the forward's TMA bulk copies pull each row from whichever GPU
+ * holds it, the backward stores each dX row into the owning GPU's gradient buffer (K2's d_grad
+ * there).  d_peer_tab / d_peer_gptr / d_peer_gstr are DEVICE arrays [n_fields][G] (int64):
+ * shard base pointers, gradient-column base pointers and per-sample strides.  Bit f of rw_mask:
+ * field f is row-wise sharded (row r on rank r % G, local row r / G); otherwise the field lives
+ * on one rank and entry [f][0] is used.  rows[] (HOST) = global row counts.                 */
+int rtf_embed_dot_peer_fwd(const int64_t* d_peer_tab, int G, uint64_t rw_mask, const int64_t* rows,
+                           int n_fields, int D, const void* d_ids, int ids_i64, int64_t B,
+                           int64_t ids_sb, int64_t ids_sf, const float* d_dense, int64_t dense_sb,
+                           float* d_out, int64_t out_sb, int out_cols, float* d_xsave,
+                           int64_t xsave_sb, int32_t* d_err, void* stream);
+int rtf_embed_dot_peer_bwd(const float* d_xsave, int64_t xsave_sb, const int64_t* rows,
+                           int n_fields, int D, const void* d_ids, int ids_i64, int64_t B,
+                           int64_t ids_sb, int64_t ids_sf, const float* d_dense, int64_t dense_sb,
+                           const float* d_gout, int64_t gout_sb, float* d_gdense,
+                           int64_t gdense_sb, const int64_t* d_peer_gptr,
+                           const int64_t* d_peer_gstr, int G, uint64_t rw_mask, int64_t sample0,
+                           void* stream);
+
 /* ---- deterministic column sum: out[c] = sum_b rowscale[b] * x[b,c] (rowscale may be NULL) ---
  * the batch-wide reductions of weight gradients (FM w, dense FM rows, attention projections);
  * replaces the atomics-based reductions TF uses for MatMul/BiasAdd gradients.              */

@@ -37,8 +37,28 @@ struct DotParams {
   long long gout_sb;
   float* xsave;  // fwd, optional: rows 1..F1-1 of every sample copied to (B, (F1-1)*D) — lets a
   long long xsave_sb;  // backward re-read rows locally when the forward pulled them over NVLink
+  // tables sharded over G GPUs, addressed through NVLink peer pointers (device arrays [F][G]):
+  // field f is row-wise sharded if bit f of rw_mask is set (row r lives on rank r % G at local
+  // row r / G), else wholly on one rank whose pointer sits in entry [f][0].
+  const long long* peer_tab;   // fwd: table shard base pointers
+  const long long* peer_gptr;  // bwd: where dX rows go: base of field f's column in rank g's buffer
+  const long long* peer_gstr;  // bwd: elements between consecutive samples in that buffer
+  unsigned long long rw_mask;
+  long long sample0;           // bwd: global index of this rank's first sample
+  int peer_G;
   int32_t* err;
 };
+
+__device__ __forceinline__ void peer_split(const DotParams& P, int f, long long id, int& g,
+                                           long long& row) {
+  if ((P.rw_mask >> f) & 1ull) {
+    g = (int)(id % P.peer_G);
+    row = id / P.peer_G;
+  } else {
+    g = 0;
+    row = id;
+  }
+}
 
 __host__ __device__ inline int dot_row_stride(int D) { return D + ((D % 8 == 0) ? 4 : 8); }
 
@@ -47,7 +67,14 @@ __device__ __forceinline__ const float* dot_src_row(const DotParams& P, long lon
   if (!P.gather || i == 0) return P.rbase[i] + b * P.rstride[i];
   const long long id = load_id((const IdT*)P.ids, b * P.ids_sb + (long long)(i - 1) * P.ids_sf,
                                P.rows[i - 1], P.err);
-  return id < 0 ? nullptr : P.table[i - 1] + id * P.D;
+  if (id < 0) return nullptr;
+  if (P.peer_tab) {
+    int g;
+    long long row;
+    peer_split(P, i - 1, id, g, row);
+    return reinterpret_cast<const float*>(P.peer_tab[(i - 1) * P.peer_G + g]) + row * P.D;
+  }
+  return P.table[i - 1] + id * P.D;
 }
 
 // stage the F1 rows of sample b into xt (row stride RS) with bulk async copies
@@ -188,6 +215,7 @@ dot_bwd_kernel(const __grid_constant__ DotParams P, int warp_floats) {
   float* xt = wbase;                // [F1][RS]
   float* S = xt + F1 * RS;          // [F1p][F1p]
   uint64_t* bar = reinterpret_cast<uint64_t*>(S + F1p * F1p);
+  long long* ids_w = reinterpret_cast<long long*>(bar + 2);  // [64] ids of this sample (peer bwd)
 
   for (int p = threadIdx.x; p < npairs; p += blockDim.x) {
     int i = (int)((1.f + sqrtf(1.f + 8.f * p)) * 0.5f);
@@ -209,6 +237,11 @@ dot_bwd_kernel(const __grid_constant__ DotParams P, int warp_floats) {
 
   for (; b < P.B; b += stride) {
     const float* g = P.gout + b * P.gout_sb;
+    if (P.peer_gptr)  // ids decide which GPU a row-wise sharded field's gradient row goes to
+      for (int f = lane; f < F1 - 1; f += 32) {
+        long long id = (long long)__ldg((const IdT*)P.ids + b * P.ids_sb + (long long)f * P.ids_sf);
+        ids_w[f] = (id < 0 || id >= P.rows[f]) ? -1 : id;
+      }
     for (int p = lane; p < npairs; p += 32) {
       const float v = __ldg(g + D + p);
       const int ij = pair_ij[p];
@@ -244,7 +277,17 @@ dot_bwd_kernel(const __grid_constant__ DotParams P, int warp_floats) {
           const int i = i0 + r;
           if (i < F1) {
             float4 v = acc[r];
-            float* dst = P.gbase[i] + b * P.gstride[i] + d0;
+            float* dst;
+            if (P.peer_gptr && i > 0) {  // straight into the owner's gradient buffer over NVLink
+              const long long id = (long long)ids_w[i - 1];
+              int gq = 0;
+              long long row;
+              if (id >= 0) peer_split(P, i - 1, id, gq, row);
+              const int e = (i - 1) * P.peer_G + gq;
+              dst = reinterpret_cast<float*>(P.peer_gptr[e]) + (P.sample0 + b) * P.peer_gstr[e] + d0;
+            } else {
+              dst = P.gbase[i] + b * P.gstride[i] + d0;
+            }
             if (i == 0) {  // out[:, :D] is X[0] itself
               v.x += __ldg(g + d0);
               v.y += __ldg(g + d0 + 1);
@@ -533,13 +576,13 @@ static int dot_fwd_impl(DotParams& P, int ids_i64, cudaStream_t st) {
 static int dot_bwd_impl(DotParams& P, int ids_i64, cudaStream_t st) {
   const int F1p = (P.F1 + 7) & ~7, RS = dot_row_stride(P.D);
   const int npairs = P.F1 * (P.F1 - 1) / 2;
-  if (dot_use_mma(P.F1, P.D)) {
+  if (dot_use_mma(P.F1, P.D) && !P.peer_gptr) {
     const int wf = 32 * dot_row_stride_bwd(P.D) + 32 * 36 + 4;
     const int cf = ((npairs + 1) / 2 + 3) & ~3;
     return ids_i64 ? dot_launch(dot_bwd_mma_kernel<int64_t>, P, wf, cf, st)
                    : dot_launch(dot_bwd_mma_kernel<int32_t>, P, wf, cf, st);
   }
-  const int warp_floats = P.F1 * RS + F1p * F1p + 4;
+  const int warp_floats = P.F1 * RS + F1p * F1p + 4 + 128;  // + mbarrier slot + 64 ids
   const int cta_floats = ((npairs + 1) / 2 + 3) & ~3;
   return ids_i64 ? dot_launch(dot_bwd_kernel<int64_t>, P, warp_floats, cta_floats, st)
                  : dot_launch(dot_bwd_kernel<int32_t>, P, warp_floats, cta_floats, st);
@@ -697,6 +740,76 @@ extern "C" int rtf_embed_dot_bwd(const float* const* tables, const int64_t* rows
     P.gbase[1 + f] = d_gemb + (long long)f * D;
     P.gstride[1 + f] = gemb_sb;
   }
+  P.B = B; P.F1 = F1; P.D = D; P.gout = d_gout; P.gout_sb = gout_sb;
+  return dot_bwd_impl(P, ids_i64, (cudaStream_t)stream);
+}
+
+// ---- tables sharded over G GPUs, rows pulled / gradients pushed through NVLink peer pointers --
+// d_peer_tab: device array [n_fields][G] of table-shard base pointers (as int64); a field whose
+// bit is set in rw_mask is row-wise sharded (row r on rank r % G at local row r / G), any other
+// field lives wholly on one rank whose pointer is entry [f][0].  rows[] (HOST) are the GLOBAL
+// row counts (bounds check).  d_xsave keeps the gathered rows for the backward.
+extern "C" int rtf_embed_dot_peer_fwd(const int64_t* d_peer_tab, int G, uint64_t rw_mask,
+                                      const int64_t* rows, int n_fields, int D, const void* d_ids,
+                                      int ids_i64, int64_t B, int64_t ids_sb, int64_t ids_sf,
+                                      const float* d_dense, int64_t dense_sb, float* d_out,
+                                      int64_t out_sb, int out_cols, float* d_xsave,
+                                      int64_t xsave_sb, int32_t* d_err, void* stream) {
+  if (!d_peer_tab || !rows || n_fields < 1 || G < 1) return RTF_E_ARG;
+  const int F1 = n_fields + 1;
+  int rc = dot_check_common(B, F1, D);
+  if (rc) return rc;
+  if (B == 0) return 0;
+  if (!d_ids || !d_dense || !d_out) return RTF_E_ARG;
+  const int need = D + F1 * (F1 - 1) / 2;
+  if (out_cols < need || out_sb < out_cols) return RTF_E_ARG;
+  if ((uintptr_t)d_dense % 16 || dense_sb % 4) return RTF_E_ALIGN;
+  if (d_xsave && ((uintptr_t)d_xsave % 16 || xsave_sb % 4 || xsave_sb < (int64_t)n_fields * D))
+    return RTF_E_ALIGN;
+  DotParams P = {};
+  for (int f = 0; f < n_fields; ++f) {
+    if (rows[f] <= 0) return RTF_E_ARG;
+    P.rows[f] = rows[f];
+  }
+  P.gather = 1; P.ids = d_ids; P.ids_sb = ids_sb; P.ids_sf = ids_sf; P.rbase[0] = d_dense;
+  P.rstride[0] = dense_sb; P.peer_tab = (const long long*)d_peer_tab; P.peer_G = G;
+  P.rw_mask = rw_mask; P.xsave = d_xsave; P.xsave_sb = xsave_sb;
+  P.B = B; P.F1 = F1; P.D = D; P.out = d_out; P.out_sb = out_sb; P.out_cols = out_cols;
+  P.err = d_err;
+  return dot_fwd_impl(P, ids_i64, (cudaStream_t)stream);
+}
+
+// backward of the above: X rows come from d_xsave (local), dX row of field f goes to
+// d_peer_gptr[f][g] + (sample0 + b) * d_peer_gstr[f][g] with g = id % G for row-wise fields, 0
+// otherwise — i.e. straight into the owning rank's gradient buffer (K2's d_grad there).
+extern "C" int rtf_embed_dot_peer_bwd(const float* d_xsave, int64_t xsave_sb, const int64_t* rows,
+                                      int n_fields, int D, const void* d_ids, int ids_i64,
+                                      int64_t B, int64_t ids_sb, int64_t ids_sf,
+                                      const float* d_dense, int64_t dense_sb, const float* d_gout,
+                                      int64_t gout_sb, float* d_gdense, int64_t gdense_sb,
+                                      const int64_t* d_peer_gptr, const int64_t* d_peer_gstr, int G,
+                                      uint64_t rw_mask, int64_t sample0, void* stream) {
+  if (!d_peer_gptr || !d_peer_gstr || !rows || n_fields < 1 || G < 1) return RTF_E_ARG;
+  const int F1 = n_fields + 1;
+  int rc = dot_check_common(B, F1, D);
+  if (rc) return rc;
+  if (B == 0) return 0;
+  if (!d_xsave || !d_ids || !d_dense || !d_gout || !d_gdense) return RTF_E_ARG;
+  if (gout_sb < D + F1 * (F1 - 1) / 2) return RTF_E_ARG;
+  if ((uintptr_t)d_dense % 16 || dense_sb % 4 || (uintptr_t)d_gdense % 16 || gdense_sb % 4 ||
+      (uintptr_t)d_xsave % 16 || xsave_sb % 4)
+    return RTF_E_ALIGN;
+  DotParams P = {};
+  for (int f = 0; f < n_fields; ++f) {
+    P.rows[f] = rows[f];
+    P.rbase[1 + f] = d_xsave + (long long)f * D;
+    P.rstride[1 + f] = xsave_sb;
+  }
+  P.rbase[0] = d_dense; P.rstride[0] = dense_sb;
+  P.gbase[0] = d_gdense; P.gstride[0] = gdense_sb;
+  P.ids = d_ids; P.ids_sb = ids_sb; P.ids_sf = ids_sf;
+  P.peer_gptr = (const long long*)d_peer_gptr; P.peer_gstr = (const long long*)d_peer_gstr;
+  P.peer_G = G; P.rw_mask = rw_mask; P.sample0 = sample0;
   P.B = B; P.F1 = F1; P.D = D; P.gout = d_gout; P.gout_sb = gout_sb;
   return dot_bwd_impl(P, ids_i64, (cudaStream_t)stream);
 }

@@ -198,6 +198,20 @@ class EmbeddingTables(torch.nn.Module):
         if optimizer is not None:
             self.set_optimizer(optimizer)
 
+    @classmethod
+    def from_tensors(cls, weights: Sequence[torch.Tensor], optimizer: Optional[SparseOptimizer] = None):
+        """Wrap existing (rows, dim) fp32 device tensors — e.g. shards living in NVLink
+        peer-mapped (symmetric) memory — without allocating or initialising anything."""
+        self = cls.__new__(cls)
+        torch.nn.Module.__init__(self)
+        self.weights = torch.nn.ParameterList([torch.nn.Parameter(w, requires_grad=False) for w in weights])
+        self.register_buffer("err", torch.zeros(1, dtype=torch.int32, device=weights[0].device))
+        self.optimizer = None
+        self.state1, self.state2 = [], []
+        if optimizer is not None:
+            self.set_optimizer(optimizer)
+        return self
+
     def set_optimizer(self, optimizer: Optional[SparseOptimizer]):
         self.optimizer = optimizer
         n = 0 if optimizer is None else optimizer.n_states

@@ -364,3 +364,237 @@ class ShardedDLRMTrainer:
             off += g.numel()
         self.dense_opt.step()
         return loss.detach()
+
+
+# =============================================================================================
+# Table-wise AND row-wise sharding with the exchange fused into K4 (exchange="peer")
+# =============================================================================================
+class PeerLayout:
+    """Placement for the peer-memory path: tables with >= `row_wise_min_rows` rows are split
+    row-wise over all ranks (row r lives on rank r % G at local row r // G — every rank then
+    serves ~1/G of that table's lookups whatever the id distribution), the rest are placed
+    table-wise by `plan_table_owners`.  fields[g] = tables with a shard on rank g (ascending);
+    a rank's gradient buffer is (B_global, len(fields[g]) * D), column block j for fields[g][j].
+    Pure host logic (tested on CPU)."""
+
+    def __init__(self, rows: Sequence[int], dims: Sequence[int], world: int,
+                 row_wise_min_rows: int = 5_000_000, row_wise: Optional[Sequence[bool]] = None,
+                 owners: Optional[Sequence[int]] = None):
+        n = len(rows)
+        if n > 64:
+            raise ValueError("at most 64 sparse fields (row-wise mask is 64 bits)")
+        self.world, self.rows, self.dims, self.n_tables = world, list(rows), list(dims), n
+        if row_wise is None:
+            row_wise = [world > 1 and rows[t] >= row_wise_min_rows for t in range(n)]
+        self.row_wise = [bool(x) for x in row_wise]
+        tw = [t for t in range(n) if not self.row_wise[t]]
+        if owners is None:
+            own_tw = plan_table_owners([rows[t] for t in tw], [dims[t] for t in tw], world)
+            owners = [-1] * n
+            for t, g in zip(tw, own_tw):
+                owners[t] = g
+        self.owners = [(-1 if self.row_wise[t] else int(owners[t])) for t in range(n)]
+        self.rw_mask = sum(1 << t for t in range(n) if self.row_wise[t])
+        self.fields = [[t for t in range(n) if self.row_wise[t] or self.owners[t] == g]
+                       for g in range(world)]
+        self.slot = [{t: j for j, t in enumerate(f)} for f in self.fields]
+
+    def local_rows(self, g: int, t: int) -> int:
+        if not self.row_wise[t]:
+            return self.rows[t]
+        return (self.rows[t] - g + self.world - 1) // self.world      # rows g, g+G, g+2G, ...
+
+    def shard_offsets(self, g: int):
+        """element offsets of rank g's shards inside its table buffer, and the total."""
+        off, acc = {}, 0
+        for t in self.fields[g]:
+            off[t] = acc
+            acc += self.local_rows(g, t) * self.dims[t]
+        return off, acc
+
+    def buffer_elems(self) -> int:
+        return max(self.shard_offsets(g)[1] for g in range(self.world))   # same size everywhere
+
+    def max_fields(self) -> int:
+        return max(len(f) for f in self.fields)
+
+    def holder(self, t: int, row: int):
+        """(rank, local row) that stores global row `row` of table t."""
+        if self.row_wise[t]:
+            return row % self.world, row // self.world
+        return self.owners[t], row
+
+    def peer_pointer_tables(self, tab_ptrs: Sequence[int], grad_ptrs: Sequence[int], D: int):
+        """HOST lists [n_tables][G] for the kernels: table-shard base addresses, gradient-column
+        base addresses and gradient sample strides (elements).  Table-wise fields use entry 0."""
+        G = self.world
+        tab = [[0] * G for _ in range(self.n_tables)]
+        gptr = [[0] * G for _ in range(self.n_tables)]
+        gstr = [[0] * G for _ in range(self.n_tables)]
+        offs = [self.shard_offsets(g)[0] for g in range(G)]
+        for t in range(self.n_tables):
+            ranks = range(G) if self.row_wise[t] else [self.owners[t]]
+            for e, g in enumerate(ranks):
+                tab[t][e] = tab_ptrs[g] + offs[g][t] * 4
+                gptr[t][e] = grad_ptrs[g] + self.slot[g][t] * D * 4
+                gstr[t][e] = len(self.fields[g]) * D
+        return tab, gptr, gstr
+
+
+def local_shard_ids(ids_global: torch.Tensor, layout: PeerLayout, rank: int) -> torch.Tensor:
+    """(B_global, n_tables) global ids -> (B_global, len(fields[rank])) ids into this rank's
+    shards; lookups of a row-wise table that another rank holds become -1 (K2 skips them)."""
+    f = layout.fields[rank]
+    idx = torch.as_tensor(f, dtype=torch.int64, device=ids_global.device)
+    loc = ids_global.index_select(1, idx)
+    rw = torch.as_tensor([layout.row_wise[t] for t in f], dtype=torch.bool, device=loc.device)
+    if bool(rw.any()):
+        G = layout.world
+        mine = (loc % G) == rank
+        loc = torch.where(rw.view(1, -1), torch.where(mine & (loc >= 0),
+                                                     torch.div(loc, G, rounding_mode="floor"),
+                                                     torch.full_like(loc, -1)), loc)
+    return loc.contiguous()
+
+
+class _PeerDotFn(torch.autograd.Function):
+    """K1+K4 over tables sharded across the GPUs of the box: the forward's TMA bulk copies pull
+    every embedding row from whichever GPU holds it (NVLink peer memory) and keep a local copy
+    for the backward; the backward stores each dX row straight into the gradient buffer of the
+    rank that owns that row.  No NCCL all-to-all, no staging buffer."""
+
+    @staticmethod
+    def forward(ctx, model: "PeerShardedDLRM", ids, dense, pad_to):
+        L.require_cuda(ids, "peer embed_dot(ids)")
+        dense = dense.contiguous()
+        lay = model.layout
+        B, F = ids.shape
+        D = dense.shape[1]
+        cols = dot_out_cols(F + 1, D, pad_to)
+        out = torch.empty((B, cols), dtype=torch.float32, device=dense.device)
+        xsave = torch.empty((B, F * D), dtype=torch.float32, device=dense.device)
+        rc = L.lib().rtf_embed_dot_peer_fwd(
+            model._d_peer_tab.data_ptr(), lay.world, lay.rw_mask, model._rows_arr, F, D,
+            ids.data_ptr(), int(ids.dtype == torch.int64), B, ids.stride(0), ids.stride(1),
+            dense.data_ptr(), dense.stride(0), out.data_ptr(), cols, cols, xsave.data_ptr(),
+            xsave.stride(0), model.embed_layers.err.data_ptr(), L.current_stream_ptr())
+        L.check(rc, "rtf_embed_dot_peer_fwd")
+        ctx.model, ctx.ids = model, ids
+        ctx.save_for_backward(dense, xsave)
+        return out
+
+    @staticmethod
+    def backward(ctx, gout):
+        dense, xsave = ctx.saved_tensors
+        model, ids = ctx.model, ctx.ids
+        lay = model.layout
+        gout = gout.contiguous()
+        B, F = ids.shape
+        D = dense.shape[1]
+        gdense = torch.empty_like(dense)
+        rc = L.lib().rtf_embed_dot_peer_bwd(
+            xsave.data_ptr(), xsave.stride(0), model._rows_arr, F, D, ids.data_ptr(),
+            int(ids.dtype == torch.int64), B, ids.stride(0), ids.stride(1), dense.data_ptr(),
+            dense.stride(0), gout.data_ptr(), gout.stride(0), gdense.data_ptr(), gdense.stride(0),
+            model._d_peer_gptr.data_ptr(), model._d_peer_gstr.data_ptr(), lay.world, lay.rw_mask,
+            model.rank * B, L.current_stream_ptr())
+        L.check(rc, "rtf_embed_dot_peer_bwd")
+        model._pending = True
+        return None, None, gdense, None
+
+
+class PeerShardedDLRM(Layer):
+    """DLRM (constructor of dlrm.DLRM) with embedding tables sharded table-wise and row-wise over
+    the GPUs of one NVSwitch box; dense MLPs data-parallel.  Every rank keeps its shards in
+    peer-mapped (symmetric) memory and the fused gather+interaction kernels address remote rows
+    directly, so the "all-to-all of pooled embeddings" happens row by row inside K4, overlapped
+    with its arithmetic.  Drives the same ShardedDLRMTrainer as ShardedDLRM."""
+
+    exchange = "peer"
+
+    def __init__(self, feature_columns, bot_dnn_hidden_units=(64, 32, 16),
+                 top_dnn_hidden_units=(128, 64), activation="relu", dnn_dropout=0.0, embed_reg=1e-4,
+                 sparse_optimizer: Optional[SparseOptimizer] = None, pad_to: int = 1,
+                 input_bn: bool = True, seed: Optional[int] = None,
+                 row_wise_min_rows: int = 5_000_000, row_wise=None, owners=None):
+        super().__init__()
+        import torch.distributed._symmetric_memory as symm
+        self.world, self.rank = dist.get_world_size(), dist.get_rank()
+        self.dense_feature_columns, self.sparse_feature_columns = feature_columns
+        rows = [f["feat_num"] for f in self.sparse_feature_columns]
+        dims = [f["embed_dim"] for f in self.sparse_feature_columns]
+        if len(set(dims)) != 1 or bot_dnn_hidden_units[-1] != dims[0]:
+            raise ValueError("dot interaction needs equal embed_dim == bot_dnn_hidden_units[-1]")
+        self.D, self.pad_to, self.embed_reg = dims[0], pad_to, embed_reg
+        self.layout = lay = PeerLayout(rows, dims, self.world, row_wise_min_rows, row_wise, owners)
+        dev = torch.device("cuda", torch.cuda.current_device())
+        # this rank's shards: views into ONE symmetric allocation every peer can address
+        self._tab_buf = symm.empty(lay.buffer_elems(), dtype=torch.float32, device=dev)
+        self._tab_hdl = symm.rendezvous(self._tab_buf, dist.group.WORLD)
+        offs, _ = lay.shard_offsets(self.rank)
+        gen = None if seed is None else torch.Generator(device=dev).manual_seed(seed + 1 + self.rank)
+        shards = []
+        for t in lay.fields[self.rank]:
+            n = lay.local_rows(self.rank, t)
+            w = self._tab_buf[offs[t]: offs[t] + n * dims[t]].view(n, dims[t])
+            w.uniform_(-0.05, 0.05, generator=gen)          # Keras 'random_uniform'
+            shards.append(w)
+        self.embed_layers = EmbeddingTables.from_tensors(shards, optimizer=sparse_optimizer)
+        if seed is not None:
+            torch.manual_seed(seed)                 # identical MLP init on every rank
+        self.bot_dnn = DNN(bot_dnn_hidden_units, activation, dnn_dropout, input_bn=input_bn)
+        self.top_dnn = DNN(top_dnn_hidden_units, activation, dnn_dropout, input_bn=input_bn)
+        self.final_dense = Dense(1, activation=None)
+        self._rows_arr = L.host_array(C.c_int64, rows)
+        self._grad_B = None
+        self._pending = False
+        self._prepared = None
+
+    def _ensure_grad_buffer(self, B_local: int):
+        if self._grad_B == B_local:
+            return
+        import torch.distributed._symmetric_memory as symm
+        lay, D = self.layout, self.D
+        dev = self._tab_buf.device
+        n = B_local * self.world * lay.max_fields() * D
+        self._grad_buf = symm.empty(n, dtype=torch.float32, device=dev)
+        self._grad_hdl = symm.rendezvous(self._grad_buf, dist.group.WORLD)
+        tab, gptr, gstr = lay.peer_pointer_tables(self._tab_hdl.buffer_ptrs,
+                                                  self._grad_hdl.buffer_ptrs, D)
+        self._d_peer_tab = torch.tensor(tab, dtype=torch.int64, device=dev)
+        self._d_peer_gptr = torch.tensor(gptr, dtype=torch.int64, device=dev)
+        self._d_peer_gstr = torch.tensor(gstr, dtype=torch.int64, device=dev)
+        self._grad_B = B_local
+
+    def call(self, inputs, **kwargs):
+        dense_inputs, sparse_inputs = inputs
+        B_local = sparse_inputs.shape[0]
+        self._ensure_grad_buffer(B_local)
+        train = torch.is_grad_enabled() and self.embed_layers.optimizer is not None
+        if train:
+            # K2 runs where the rows live: every rank needs the ids of the global batch for its
+            # shards (104 B/sample).  Keys, sort and segments start now on a side stream.
+            ids_global = exchange_ids(sparse_inputs, self.world)
+            loc = local_shard_ids(ids_global, self.layout, self.rank)
+            self._prepared = self.embed_layers.prepare_backward(loc, list(range(loc.shape[1])))
+        dense_fea = self.bot_dnn(dense_inputs)
+        # every rank's row updates of the previous step are complete before anyone pulls rows
+        self._tab_hdl.barrier(channel=0)
+        x = _PeerDotFn.apply(self, sparse_inputs, dense_fea, self.pad_to)
+        return torch.sigmoid(self.final_dense(self.top_dnn(x)))
+
+    def finish_backward(self):
+        """All peers' dX rows have landed in this rank's gradient buffer -> K2 (+ sparse optimizer)
+        on the local shards."""
+        if not self._pending:
+            return
+        self._grad_hdl.barrier(channel=0)
+        Tme = len(self.layout.fields[self.rank])
+        Bg = self._grad_B * self.world
+        grad = self._grad_buf[: Bg * Tme * self.D].view(Bg, Tme * self.D)
+        self.embed_layers.apply_prepared(self._prepared, grad)
+        self._pending, self._prepared = False, None
+
+    def dense_parameters(self):
+        emb = {id(p) for p in self.embed_layers.parameters()}
+        return [p for p in self.parameters() if id(p) not in emb]

@@ -8,7 +8,7 @@ import torch.distributed as dist
 
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import recommend_tf2_b200 as pkg  # noqa: E402
-from recommend_tf2_b200.sharded import ShardedDLRM, ShardedDLRMTrainer  # noqa: E402
+from recommend_tf2_b200.sharded import PeerShardedDLRM, ShardedDLRM, ShardedDLRMTrainer  # noqa: E402
 
 
 def main():
@@ -21,9 +21,22 @@ def main():
     fc = [[{"feat": f"I{i}"} for i in range(13)],
           [{"feat": f"C{t}", "feat_num": rows[t], "embed_dim": D} for t in range(F)]]
     kw = dict(bot_dnn_hidden_units=(64, D), top_dnn_hidden_units=(128, 64), input_bn=False)
-    mode = os.environ.get("RTF_EXCHANGE", "p2p")
+    mode = os.environ.get("RTF_EXCHANGE", "peer")
     single = pkg.DLRM(fc, seed=5, **kw)
-    sharded = ShardedDLRM(fc, seed=5, exchange=mode, **kw)
+    if mode == "peer":   # tables with >= 200 rows are split row-wise, the rest placed table-wise
+        sharded = PeerShardedDLRM(fc, seed=5, row_wise_min_rows=200, **kw)
+        lay = sharded.layout
+        assert any(lay.row_wise) and not all(lay.row_wise)
+        mine = lay.fields[rank]
+
+        def shard_of(w, t):
+            return w[rank::world] if lay.row_wise[t] else w
+    else:
+        sharded = ShardedDLRM(fc, seed=5, exchange=mode, **kw)
+        mine = sharded.layout.slots[rank]
+
+        def shard_of(w, t):
+            return w
     g = torch.Generator(device="cuda").manual_seed(99)
     B = B_local * world
     dense = torch.rand(B, 13, device="cuda", generator=g)
@@ -35,8 +48,8 @@ def main():
     with torch.no_grad():
         single([dense, sparse])
         sharded([dense[sl], sparse[sl]])
-        for j, t in enumerate(sharded.layout.slots[rank]):
-            sharded.embed_layers.weights[j].copy_(single.embed_layers.weights[t])
+        for j, t in enumerate(mine):
+            sharded.embed_layers.weights[j].copy_(shard_of(single.embed_layers.weights[t], t))
         for ps, pd in zip(single.dense_parameters(), sharded.dense_parameters()):
             pd.copy_(ps)
         p1 = single([dense, sparse])
@@ -51,15 +64,18 @@ def main():
     lsum = l2.clone()
     dist.all_reduce(lsum)
     torch.testing.assert_close(lsum / world, l1, rtol=1e-5, atol=1e-6)
-    for j, t in enumerate(sharded.layout.slots[rank]):
-        torch.testing.assert_close(sharded.embed_layers.weights[j], single.embed_layers.weights[t],
-                                   rtol=1e-4, atol=2e-6)
+    for j, t in enumerate(mine):
+        torch.testing.assert_close(sharded.embed_layers.weights[j],
+                                   shard_of(single.embed_layers.weights[t], t), rtol=1e-4, atol=2e-6)
+        torch.testing.assert_close(sharded.embed_layers.state1[j],
+                                   shard_of(single.embed_layers.state1[t], t), rtol=1e-4, atol=1e-7)
     for ps, pd in zip(single.dense_parameters(), sharded.dense_parameters()):
         torch.testing.assert_close(pd, ps, rtol=1e-4, atol=2e-6)
     sharded.embed_layers.check_ids()
     dist.barrier()
     if rank == 0:
-        print(f"mgpu_check ok: world={world} exchange={mode} owners={sharded.layout.owners}")
+        print(f"mgpu_check ok: world={world} exchange={mode} owners={sharded.layout.owners}"
+              + (f" row_wise={[t for t in range(F) if sharded.layout.row_wise[t]]}" if mode == "peer" else ""))
     dist.destroy_process_group()
 
 

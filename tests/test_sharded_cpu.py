@@ -85,3 +85,74 @@ def _worker(rank, world, port, F, D, B_local):
 @pytest.mark.parametrize("world,F", [(2, 5), (2, 26), (3, 7)])
 def test_exchange_round_trip_gloo(world, F):
     mp.spawn(_worker, args=(world, _free_port(), F, 4, 3), nprocs=world, join=True)
+
+
+# ---- table-wise + row-wise placement of the peer-memory path (host logic only) ---------------
+from recommend_tf2_b200.sharded import PeerLayout, local_shard_ids  # noqa: E402
+
+
+@pytest.mark.parametrize("world", [1, 2, 4, 8])
+def test_peer_layout_row_wise_and_table_wise(world):
+    lay = PeerLayout(CRITEO, [128] * 26, world)
+    big = [t for t in range(26) if CRITEO[t] >= 5_000_000]
+    assert len(big) == 4
+    assert [t for t in range(26) if lay.row_wise[t]] == (big if world > 1 else [])
+    assert lay.rw_mask == sum(1 << t for t in big) * (world > 1)
+    # every table-wise table has exactly one owner, every row-wise table a shard on every rank
+    for t in range(26):
+        holders = [g for g in range(world) if t in lay.fields[g]]
+        assert holders == (list(range(world)) if lay.row_wise[t] else [lay.owners[t]])
+        assert sum(lay.local_rows(g, t) for g in holders) == CRITEO[t]
+    counts = [len(f) for f in lay.fields]
+    assert max(counts) - min(counts) <= 1
+    # shard bytes are balanced now that the multi-million-row tables are split
+    sizes = [lay.shard_offsets(g)[1] for g in range(world)]
+    assert lay.buffer_elems() == max(sizes)
+    if world > 1:
+        assert max(sizes) < 1.5 * (sum(sizes) / world)    # the 2.2 M-row table stays whole
+    # pointer tables: one distinct, 16-byte aligned address per shard / gradient column
+    tab_ptrs = [(g + 1) << 40 for g in range(world)]
+    grad_ptrs = [(g + 101) << 40 for g in range(world)]
+    tab, gptr, gstr = lay.peer_pointer_tables(tab_ptrs, grad_ptrs, 128)
+    seen = set()
+    for t in range(26):
+        n = world if lay.row_wise[t] else 1
+        for e in range(n):
+            g = e if lay.row_wise[t] else lay.owners[t]
+            assert tab[t][e] >> 40 == g + 1 and tab[t][e] % 16 == 0
+            assert gptr[t][e] >> 40 == g + 101 and gptr[t][e] % 16 == 0
+            assert gstr[t][e] == len(lay.fields[g]) * 128
+            seen.add(tab[t][e])
+            seen.add(gptr[t][e])
+    assert len(seen) == 2 * sum(world if lay.row_wise[t] else 1 for t in range(26))
+
+
+@pytest.mark.parametrize("world", [2, 3, 8])
+def test_local_shard_ids_partition_every_lookup_once(world):
+    rows = [7, 1000, 13, 4097, 5]
+    lay = PeerLayout(rows, [8] * 5, world, row_wise_min_rows=1000)
+    assert lay.row_wise == [False, True, False, True, False]
+    g = torch.Generator().manual_seed(world)
+    B = 257
+    ids = torch.stack([torch.randint(0, r, (B,), generator=g) for r in rows], 1).to(torch.int32)
+    ids[3, 1] = -1            # invalid ids stay invalid on every rank
+    ids[5, 3] = 4097
+    hits = torch.zeros(B, 5, dtype=torch.int32)
+    for rank in range(world):
+        loc = local_shard_ids(ids, lay, rank)
+        assert loc.dtype == torch.int32 and loc.shape == (B, len(lay.fields[rank]))
+        for j, t in enumerate(lay.fields[rank]):
+            col = loc[:, j]
+            ok = (col >= 0) & (col < lay.local_rows(rank, t))
+            hits[:, t] += ok.int()
+            if lay.row_wise[t]:      # local row maps back to the global row, on this rank
+                back = col[ok].long() * world + rank
+                assert torch.equal(back, ids[ok, t].long())
+                for b in torch.nonzero(ok).flatten()[:20].tolist():
+                    assert lay.holder(t, int(ids[b, t])) == (rank, int(col[b]))
+            else:
+                assert torch.equal(col, ids[:, t])
+    want = torch.ones(B, 5, dtype=torch.int32)
+    want[3, 1] = 0
+    want[5, 3] = 0
+    assert torch.equal(hits, want)

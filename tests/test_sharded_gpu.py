@@ -1,4 +1,4 @@
-"""Sharded (table-wise model-parallel) DLRM == single-GPU DLRM; needs >= 2 GPUs on the box."""
+"""Sharded DLRM (table-wise + row-wise model parallel) == single-GPU DLRM; needs >= 2 GPUs."""
 import os
 import subprocess
 import sys
@@ -10,12 +10,14 @@ pytestmark = pytest.mark.gpu
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
 
-def test_sharded_dlrm_matches_single_gpu(rtf):
+@pytest.mark.parametrize("mode", ["peer", "p2p", "nccl"])
+def test_sharded_dlrm_matches_single_gpu(rtf, mode):
     n = torch.cuda.device_count()
     if n < 2:
         pytest.skip("needs >= 2 GPUs")
     cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", f"--nproc-per-node={min(n, 4)}",
            "--master-addr", "127.0.0.1", "--master-port", "29711",
            os.path.join(ROOT, "tests", "mgpu_check.py")]
-    res = subprocess.run(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True, timeout=600)
+    res = subprocess.run(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True, timeout=600,
+                         env=dict(os.environ, RTF_EXCHANGE=mode))
     assert res.returncode == 0 and "mgpu_check ok" in res.stdout, res.stdout[-3000:]
