@@ -42,8 +42,9 @@ def parse_args():
     ap.add_argument("--ids", default="uniform", choices=["uniform", "zipf"])
     ap.add_argument("--cpu-batch", type=int, default=2048)
     ap.add_argument("--cpu-row-cap", type=int, default=1_000_000)
-    ap.add_argument("--mlp-gemm", default="bf16x9", choices=["bf16x9", "native"],
-                    help="dense-MLP GEMMs: cuBLAS 12.9 FP32 emulation (BF16x9, fp32-accurate) or SGEMM")
+    ap.add_argument("--mlp-gemm", default="bf16x6", choices=["bf16x6", "bf16x9", "native"],
+                    help="dense-MLP GEMMs: librtf_b200's tcgen05 GEMM (fp32 split into 3 bf16 terms, 6 "
+                         "products, fp32-accurate), cuBLAS 12.9 FP32 emulation (BF16x9), or SGEMM")
     ap.add_argument("--pad-to", type=int, default=8, help="round the interaction width up (479 -> 480)")
     ap.add_argument("--exchange", default="peer", choices=["peer", "p2p", "nccl"],
                     help="multi-GPU row exchange: 'peer' = tables sharded table-wise + row-wise, rows "
@@ -281,6 +282,10 @@ def run_b200(args):
     gemm_desc = "native fp32 SGEMM (cuBLAS bundled with torch)"
     if args.mlp_gemm == "bf16x9":
         gemm_desc = preload_cublas_fp32_emulation()
+    elif args.mlp_gemm == "bf16x6":
+        gemm_desc = ("librtf_b200 tcgen05 GEMM: fp32 operands split into 3 bf16 terms, 6 products "
+                     "(fp32-accurate, ~2e-7 vs fp64), fp32 in/out; 13-wide first layer and 1-wide "
+                     "last layer on cuBLAS SGEMM")
     import torch
     import torch.distributed as dist
 
@@ -298,6 +303,8 @@ def run_b200(args):
 
     import recommend_tf2_b200 as pkg
     pkg.lib()
+    from recommend_tf2_b200 import core as _core
+    _core.set_dense_gemm("bf16x6" if args.mlp_gemm == "bf16x6" else "library")
     peaks, peak_src = load_peaks()
 
     B = args.batch

@@ -299,6 +299,36 @@ int rtf_relu_bwd_colsum_workspace(int64_t B, int cols, size_t* bytes);
 int rtf_relu_bwd_colsum(const float* d_gy, const float* d_y, int64_t B, int cols, float* d_g,
                         float* d_colsum, void* d_ws, void* stream);
 
+/* ---- dense-layer GEMMs (MLP either side of the path) --------------------------
+ * replaces: the MatMul (+BiasAdd+Relu) of tensorflow.keras.layers.Dense inside
+ *           ctr.layers.modules.DNN (src/ctr/layers/modules.py:114-135) and its two gradient
+ *           MatMuls.  fp32 in / fp32 out on the tcgen05 tensor cores: operands are split on the
+ *           fly into 3 bf16 terms and the 6 partial products weighing >= 2^-16 are accumulated
+ *           in fp32 (error ~1e-7 relative, an fp32-grade GEMM; csrc/dense_gemm.cuh).
+ * out[l] (M x N row-major, ldd) = act(A[l] * B[l] + bias[n]),  act = ReLU if relu else identity,
+ * bias may be NULL; l = 0..batch-1 with element strides stride_* between batch items.
+ *   _nn : A (M x K) row-major lda,  B (K x N) row-major ldb        forward   y = x W
+ *   _nt : A (M x K) row-major lda,  B (N x K) row-major ldb        dgrad     dx = dy W^T
+ *   _tn : A (K x M) row-major lda,  B (K x N) row-major ldb        wgrad     dW = x^T dy
+ *         (batch > 1 = fixed split of the K = batch*K_chunk reduction; the caller sums the
+ *          partial outputs in order, which keeps the result deterministic)
+ * All leading dimensions / strides % 4 == 0, pointers 16-byte aligned, else RTF_E_ALIGN.     */
+int rtf_dense_gemm_nn_workspace(int M, int N, int K, int batch, size_t* bytes);
+int rtf_dense_gemm_nt_workspace(int M, int N, int K, int batch, size_t* bytes);
+int rtf_dense_gemm_tn_workspace(int M, int N, int K, int batch, size_t* bytes);
+int rtf_dense_gemm_nn(const float* d_a, int64_t lda, int64_t stride_a, const float* d_b, int64_t ldb,
+                      int64_t stride_b, const float* d_bias, int relu, float* d_out, int64_t ldd,
+                      int64_t stride_d, int M, int N, int K, int batch, void* d_ws, size_t ws_bytes,
+                      void* stream);
+int rtf_dense_gemm_nt(const float* d_a, int64_t lda, int64_t stride_a, const float* d_b, int64_t ldb,
+                      int64_t stride_b, const float* d_bias, int relu, float* d_out, int64_t ldd,
+                      int64_t stride_d, int M, int N, int K, int batch, void* d_ws, size_t ws_bytes,
+                      void* stream);
+int rtf_dense_gemm_tn(const float* d_a, int64_t lda, int64_t stride_a, const float* d_b, int64_t ldb,
+                      int64_t stride_b, const float* d_bias, int relu, float* d_out, int64_t ldd,
+                      int64_t stride_d, int M, int N, int K, int batch, void* d_ws, size_t ws_bytes,
+                      void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -63,6 +63,15 @@ SIGNATURES = {
     "rtf_colsum": [_p, _i64, _p, _i64, _int, _p, _p, _p],
     "rtf_relu_bwd_colsum_workspace": [_i64, _int, C.POINTER(C.c_size_t)],
     "rtf_relu_bwd_colsum": [_p, _p, _i64, _int, _p, _p, _p, _p],
+    "rtf_dense_gemm_nn_workspace": [_int, _int, _int, _int, C.POINTER(C.c_size_t)],
+    "rtf_dense_gemm_nt_workspace": [_int, _int, _int, _int, C.POINTER(C.c_size_t)],
+    "rtf_dense_gemm_tn_workspace": [_int, _int, _int, _int, C.POINTER(C.c_size_t)],
+    "rtf_dense_gemm_nn": [_p, _i64, _i64, _p, _i64, _i64, _p, _int, _p, _i64, _i64, _int, _int, _int,
+                          _int, _p, C.c_size_t, _p],
+    "rtf_dense_gemm_nt": [_p, _i64, _i64, _p, _i64, _i64, _p, _int, _p, _i64, _i64, _int, _int, _int,
+                          _int, _p, C.c_size_t, _p],
+    "rtf_dense_gemm_tn": [_p, _i64, _i64, _p, _i64, _i64, _p, _int, _p, _i64, _i64, _int, _int, _int,
+                          _int, _p, C.c_size_t, _p],
     "rtf_fm_layer_workspace": [_i64, _int, C.POINTER(C.c_size_t)],
     "rtf_fm_layer_fwd": [_p, _i64, _p, _int, _p, _i64, _int, _int, _i64, _int, _int, _p, _p, _p],
     "rtf_fm_layer_bwd": [_p, _i64, _p, _int, _p, _i64, _int, _int, _i64, _int, _int, _p, _p,

@@ -144,12 +144,87 @@ class Dense(Layer):
         return self.activation(y) if self.activation is not None else y
 
 
+# Dense GEMM backend: "bf16x6" = librtf_b200's tcgen05 GEMM (fp32 operands split into 3 bf16 terms,
+# the 6 partial products above one fp32 ulp accumulated in fp32; csrc/dense_gemm.cuh), "library" =
+# the framework's GEMM (cuBLAS).  Shapes the tensor-core path does not take (K or N not a multiple
+# of 4, tiny problems, CPU tensors) always use the library.
+import os as _os
+
+DENSE_GEMM = _os.environ.get("RTF_DENSE_GEMM", "bf16x6")
+
+
+def set_dense_gemm(kind: str) -> None:
+    global DENSE_GEMM
+    if kind not in ("bf16x6", "library"):
+        raise ValueError(kind)
+    DENSE_GEMM = kind
+
+
+def _x6_ok(*mats) -> bool:
+    if DENSE_GEMM != "bf16x6":
+        return False
+    for m in mats:
+        if not (m.is_cuda and m.dtype == torch.float32 and m.dim() == 2 and m.is_contiguous()
+                and m.shape[0] % 4 == 0 and m.shape[1] % 4 == 0 and m.data_ptr() % 16 == 0):
+            return False
+    return True
+
+
+def dense_gemm(kind: str, a: torch.Tensor, b: torch.Tensor, bias=None, relu: bool = False,
+               splits: int = 1) -> torch.Tensor:
+    """librtf_b200 fp32-accurate tensor-core GEMM on contiguous 2-D fp32 CUDA tensors.
+    kind 'nn': a (M,K) @ b (K,N) [+ bias, ReLU];  'nt': a (M,K) @ b (N,K)^T;
+    'tn': a (K,M)^T @ b (K,N), optionally as `splits` partial products over K summed in order."""
+    import ctypes as C
+    from . import _lib as L
+    lib = L.lib()
+    if kind == "nn":
+        (M, K), N = a.shape, b.shape[1]
+    elif kind == "nt":
+        (M, K), N = a.shape, b.shape[0]
+    elif kind == "tn":
+        (K, M), N = a.shape, b.shape[1]
+    else:
+        raise ValueError(kind)
+    fn = getattr(lib, f"rtf_dense_gemm_{kind}")
+    wsq = getattr(lib, f"rtf_dense_gemm_{kind}_workspace")
+    lda, ldb = a.stride(0), b.stride(0)
+    sa = sb = sd = 0
+    batch = 1
+    if kind == "tn" and splits > 1:
+        if K % splits or (K // splits) % 4:
+            raise ValueError("splits must divide K into multiples of 4")
+        batch, K = splits, K // splits
+        sa, sb, sd = K * lda, K * ldb, M * N
+    out = torch.empty((batch, M, N) if batch > 1 else (M, N), dtype=torch.float32, device=a.device)
+    nb = C.c_size_t(0)
+    L.check(wsq(M, N, K, batch, C.byref(nb)), f"rtf_dense_gemm_{kind}_workspace")
+    ws = torch.empty(max(nb.value, 16), dtype=torch.uint8, device=a.device)
+    rc = fn(a.data_ptr(), lda, sa, b.data_ptr(), ldb, sb, None if bias is None else bias.data_ptr(),
+            int(relu), out.data_ptr(), N, sd, M, N, K, batch, ws.data_ptr(), ws.numel(),
+            L.current_stream_ptr())
+    L.check(rc, f"rtf_dense_gemm_{kind}")
+    return out.sum(0) if batch > 1 else out
+
+
+def _wgrad_splits(B: int, kin: int, n: int) -> int:
+    """Split count for dW = x^T g: the reduction runs over the batch while the output is only a
+    few 256x128 tiles, so the K loop is cut into fixed chunks until every SM pair has work."""
+    tiles = ((kin + 255) // 256) * ((n + 127) // 128)
+    s = 1
+    while s * tiles < 148 and s < 64 and B % (2 * s) == 0 and B // (2 * s) >= 512:
+        s *= 2
+    return s
+
+
 def _wgrad(x: torch.Tensor, g: torch.Tensor) -> torch.Tensor:
     """dW = x^T g for a tall batch.  The reduction runs over the batch (K = 65 536 here) while the
-    output is only a few 128x128 tiles, so a single library GEMM leaves most SMs idle; a batched
+    output is only a few 128x128 tiles, so a single GEMM leaves most SMs idle; a batched
     split-K (fixed chunking, partials summed in order => deterministic) measured 2-2.6x faster
     (tools/probe_wgrad.py)."""
     B = x.shape[0]
+    if B >= 1024 and _x6_ok(x, g):
+        return dense_gemm("tn", x, g, splits=_wgrad_splits(B, x.shape[1], g.shape[1]))
     S = 16
     if B >= 8192 and B % S == 0 and x.is_contiguous() and g.is_contiguous():
         return torch.bmm(x.view(S, B // S, -1).transpose(1, 2), g.view(S, B // S, -1)).sum(0)
@@ -183,7 +258,10 @@ class _DenseFn(torch.autograd.Function):
 
     @staticmethod
     def forward(ctx, x, w, b, relu):
-        y = torch._addmm_activation(b, x, w, use_gelu=False) if relu else torch.addmm(b, x, w)
+        if x.shape[0] >= 1024 and _x6_ok(x, w) and b.data_ptr() % 16 == 0:
+            y = dense_gemm("nn", x, w, b, relu)
+        else:
+            y = torch._addmm_activation(b, x, w, use_gelu=False) if relu else torch.addmm(b, x, w)
         ctx.save_for_backward(x, w, y if relu else None)
         ctx.relu = relu
         return y
@@ -192,7 +270,9 @@ class _DenseFn(torch.autograd.Function):
     def backward(ctx, gy):
         x, w, y = ctx.saved_tensors
         g, gb = _relu_bwd_bias_grad(gy, y if ctx.relu else None)
-        gx = g @ w.t() if ctx.needs_input_grad[0] else None
+        gx = None
+        if ctx.needs_input_grad[0]:
+            gx = dense_gemm("nt", g, w) if (g.shape[0] >= 1024 and _x6_ok(g, w)) else g @ w.t()
         gw = _wgrad(x, g) if ctx.needs_input_grad[1] else None
         return gx, gw, gb, None
 
