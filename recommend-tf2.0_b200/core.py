@@ -207,14 +207,20 @@ def dense_gemm(kind: str, a: torch.Tensor, b: torch.Tensor, bias=None, relu: boo
     return out.sum(0) if batch > 1 else out
 
 
-def _wgrad_splits(B: int, kin: int, n: int) -> int:
+def _wgrad_splits(B: int, kin: int, n: int, clusters: int = 74) -> int:
     """Split count for dW = x^T g: the reduction runs over the batch while the output is only a
-    few 256x128 tiles, so the K loop is cut into fixed chunks until every SM pair has work."""
+    few 256x128 tiles, so the K loop is cut into fixed chunks (>= 512 rows) until the tiles fill
+    the 74 SM pairs with the least wave quantisation (e.g. 1024x1024: 32 tiles x 16 = 6.9 waves)."""
     tiles = ((kin + 255) // 256) * ((n + 127) // 128)
+    best, best_eff = 1, 0.0
     s = 1
-    while s * tiles < 148 and s < 64 and B % (2 * s) == 0 and B // (2 * s) >= 512:
+    while s <= 64 and B % s == 0 and (B // s) % 4 == 0 and B // s >= 512:
+        waves = tiles * s / clusters
+        eff = waves / -(-tiles * s // clusters)
+        if eff > best_eff + 0.02:
+            best, best_eff = s, eff
         s *= 2
-    return s
+    return best
 
 
 def _wgrad(x: torch.Tensor, g: torch.Tensor) -> torch.Tensor:

@@ -254,23 +254,34 @@ dot_bwd_kernel(const __grid_constant__ DotParams P, int warp_floats) {
     parity ^= 1;
     for (int d0 = lane * 4; d0 < D; d0 += 128) {
       for (int i0 = 0; i0 < F1; i0 += 8) {
-        // (packed FFMA2 with a duplicated {s,s} operand was measured slower here: the doubled S
-        //  tile costs two warps of occupancy and twice the shared loads)
-        float4 acc[8];
+        // packed fp32x2 FMAs (sm_100 FFMA2), pairing ROWS: acc2[rp][c] = {dX[i0+2rp][d0+c],
+        // dX[i0+2rp+1][d0+c]}; the S pairs come straight out of the 128-bit loads and only the 4
+        // x values are duplicated in registers (a duplicated {s,s} tile in shared memory was
+        // measured slower: two warps of occupancy and twice the shared loads)
+        float2 acc2[4][4];
 #pragma unroll
-        for (int r = 0; r < 8; ++r) acc[r] = make_float4(0.f, 0.f, 0.f, 0.f);
+        for (int rp = 0; rp < 4; ++rp)
+#pragma unroll
+          for (int c = 0; c < 4; ++c) acc2[rp][c] = make_float2(0.f, 0.f);
+#pragma unroll 3
         for (int j = 0; j < F1; ++j) {
           const float4 xj = *reinterpret_cast<const float4*>(xt + j * RS + d0);
           const float4 s0 = *reinterpret_cast<const float4*>(S + j * F1p + i0);
           const float4 s1 = *reinterpret_cast<const float4*>(S + j * F1p + i0 + 4);
-          const float s[8] = {s0.x, s0.y, s0.z, s0.w, s1.x, s1.y, s1.z, s1.w};
+          const float2 sp[4] = {make_float2(s0.x, s0.y), make_float2(s0.z, s0.w),
+                                make_float2(s1.x, s1.y), make_float2(s1.z, s1.w)};
+          const float2 xx[4] = {make_float2(xj.x, xj.x), make_float2(xj.y, xj.y),
+                                make_float2(xj.z, xj.z), make_float2(xj.w, xj.w)};
 #pragma unroll
-          for (int r = 0; r < 8; ++r) {
-            acc[r].x = fmaf(s[r], xj.x, acc[r].x);
-            acc[r].y = fmaf(s[r], xj.y, acc[r].y);
-            acc[r].z = fmaf(s[r], xj.z, acc[r].z);
-            acc[r].w = fmaf(s[r], xj.w, acc[r].w);
-          }
+          for (int rp = 0; rp < 4; ++rp)
+#pragma unroll
+            for (int c = 0; c < 4; ++c) acc2[rp][c] = __ffma2_rn(sp[rp], xx[c], acc2[rp][c]);
+        }
+        float4 acc[8];
+#pragma unroll
+        for (int rp = 0; rp < 4; ++rp) {
+          acc[2 * rp] = make_float4(acc2[rp][0].x, acc2[rp][1].x, acc2[rp][2].x, acc2[rp][3].x);
+          acc[2 * rp + 1] = make_float4(acc2[rp][0].y, acc2[rp][1].y, acc2[rp][2].y, acc2[rp][3].y);
         }
 #pragma unroll
         for (int r = 0; r < 8; ++r) {

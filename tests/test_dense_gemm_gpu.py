@@ -82,3 +82,21 @@ def test_dense_layer_matches_library_path(rtf):
     core.set_dense_gemm("bf16x6")
     for a, b in zip(res["library"], res["bf16x6"]):
         torch.testing.assert_close(b, a, rtol=1e-5, atol=1e-5 * float(a.abs().max()))
+
+
+@pytest.mark.parametrize("B,N", [(65536, 256), (5000, 128), (130, 4), (1, 1024)])
+@pytest.mark.parametrize("masked", [True, False])
+def test_relu_mask_and_bias_grad_one_pass(rtf, B, N, masked):
+    """rtf_relu_bwd_colsum: g = gy * (y > 0) bit-exact, column sums == fp64 sums to fp32 accuracy
+    and identical from run to run (fixed two-stage order)."""
+    g = torch.Generator(device="cuda").manual_seed(B + N)
+    gy = torch.randn(B, N, device="cuda", generator=g)
+    y = torch.randn(B, N, device="cuda", generator=g).clamp_min(0) if masked else None
+    got_g, got_db = core._relu_bwd_bias_grad(gy, y)
+    want_g = gy * (y > 0) if masked else gy
+    assert torch.equal(got_g, want_g)
+    want_db = want_g.double().sum(0)
+    scale = float(want_g.double().abs().sum(0).max()) + 1e-30
+    assert float((got_db.double() - want_db).abs().max()) / scale < 1e-6
+    _, again = core._relu_bwd_bias_grad(gy, y)
+    assert torch.equal(got_db, again)
