@@ -69,18 +69,10 @@ def make_batches(n, B, rows, ids_kind, seed):
     (B,26) i32 (uniform or Zipf(1.05) mod N_t), labels Bernoulli(0.25)."""
     import numpy as np
     import torch
+    from recommend_tf2_b200.data import synthetic_criteo_batch
     rng = np.random.default_rng(seed)
-    out = []
-    for _ in range(n):
-        dense = rng.random((B, N_DENSE), dtype=np.float32)
-        if ids_kind == "uniform":
-            sparse = np.stack([rng.integers(0, r, B, dtype=np.int64) for r in rows], 1)
-        else:
-            sparse = np.stack([(rng.zipf(1.05, B) - 1) % r for r in rows], 1)
-        y = (rng.random((B, 1)) < 0.25).astype(np.float32)
-        out.append((torch.from_numpy(dense), torch.from_numpy(sparse.astype(np.int32)),
-                    torch.from_numpy(y)))
-    return out
+    return [tuple(torch.from_numpy(a) for a in synthetic_criteo_batch(rng, B, rows, ids_kind))
+            for _ in range(n)]
 
 
 class ClockSampler:
@@ -309,8 +301,7 @@ def run_b200(args):
 
     B = args.batch
     K, W = args.steps, max(args.warmup, 3)
-    fc = [[{"feat": f"I{i}"} for i in range(N_DENSE)],
-          [{"feat": f"C{i}", "feat_num": r, "embed_dim": EMBED_DIM} for i, r in enumerate(CRITEO_ROWS)]]
+    fc = pkg.criteo_feature_columns(EMBED_DIM, rows=CRITEO_ROWS)
     if world == 1:
         model = pkg.DLRM(fc, BOT_MLP, TOP_MLP, interaction="dot", seed=1234, pad_to=args.pad_to)
         trainer = pkg.DLRMTrainer(model, lr=1e-3)
@@ -352,10 +343,10 @@ def run_b200(args):
     barrier()
     f0, f1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     f0.record()
-    for i in range(W, W + K):
-        d, s, y = (t.cuda(non_blocking=True) for t in host[i])
+    # the public input path: pinned host batches -> DeviceFeeder (copy stream, one step ahead)
+    for i, (d, s, y) in enumerate(pkg.DeviceFeeder(host[W:W + K])):
         loss = trainer.step(d, s, y)
-        loss_host[i - W].copy_(loss, non_blocking=True)
+        loss_host[i].copy_(loss, non_blocking=True)
     f1.record()
     barrier()
     ms_e2e = f0.elapsed_time(f1)

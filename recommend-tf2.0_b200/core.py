@@ -264,6 +264,15 @@ class _DenseFn(torch.autograd.Function):
 
     @staticmethod
     def forward(ctx, x, w, b, relu):
+        kpad = 0
+        if (x.shape[1] % 4 and DENSE_GEMM == "bf16x6" and x.is_cuda and x.shape[0] >= 1024
+                and w.shape[1] % 4 == 0 and x.shape[0] % 4 == 0):
+            # e.g. the 13 dense Criteo features: zero-pad K to a multiple of 4 (16-byte rows for
+            # TMA) so this layer runs on the tensor-core path too; the pad is sliced off again
+            kpad = (-x.shape[1]) % 4
+            x = F.pad(x, (0, kpad))
+            w = F.pad(w, (0, 0, 0, kpad))
+        ctx.kpad = kpad
         if x.shape[0] >= 1024 and _x6_ok(x, w) and b.data_ptr() % 16 == 0:
             y = dense_gemm("nn", x, w, b, relu)
         else:
@@ -280,6 +289,9 @@ class _DenseFn(torch.autograd.Function):
         if ctx.needs_input_grad[0]:
             gx = dense_gemm("nt", g, w) if (g.shape[0] >= 1024 and _x6_ok(g, w)) else g @ w.t()
         gw = _wgrad(x, g) if ctx.needs_input_grad[1] else None
+        if ctx.kpad:
+            gx = None if gx is None else gx[:, : gx.shape[1] - ctx.kpad]
+            gw = None if gw is None else gw[: gw.shape[0] - ctx.kpad]
         return gx, gw, gb, None
 
 

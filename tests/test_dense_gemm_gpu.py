@@ -100,3 +100,23 @@ def test_relu_mask_and_bias_grad_one_pass(rtf, B, N, masked):
     assert float((got_db.double() - want_db).abs().max()) / scale < 1e-6
     _, again = core._relu_bwd_bias_grad(gy, y)
     assert torch.equal(got_db, again)
+
+
+def test_dense_layer_unaligned_input_width_is_padded(rtf):
+    """13 dense features (K % 4 != 0): the layer zero-pads K for the tensor-core path and returns
+    gradients of the original shapes, equal to the framework path's."""
+    g = torch.Generator(device="cuda").manual_seed(13)
+    x = torch.rand(4096, 13, device="cuda", generator=g, requires_grad=True)
+    res = {}
+    for kind in ("library", "bf16x6"):
+        core.set_dense_gemm(kind)
+        torch.manual_seed(1)
+        layer = core.Dense(512, activation="relu")
+        y = layer(x)
+        (y * y).sum().backward()
+        res[kind] = (y.detach(), x.grad.clone(), layer.kernel.grad.clone(), layer.bias.grad.clone())
+        assert x.grad.shape == (4096, 13) and layer.kernel.grad.shape == (13, 512)
+        x.grad = None
+    core.set_dense_gemm("bf16x6")
+    for a, b in zip(res["library"], res["bf16x6"]):
+        torch.testing.assert_close(b, a, rtol=1e-5, atol=1e-5 * float(a.abs().max()))
