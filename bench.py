@@ -363,10 +363,19 @@ def run_b200(args):
         roof = None
         if not args.no_kernel_timing and world == 1:
             kernels = time_kernels(pkg, model, dev[W:W + min(K, 8)], peaks["hbm_gbs"])
+            # DRAM traffic per launch from the committed `ncu --set full` capture of the same kernels on
+            # the same workload (profiles/r1_ncu_traffic.json); null when a kernel was not captured
+            traffic = {}
+            tpath = os.path.join(ROOT, "profiles", "r1_ncu_traffic.json")
+            if os.path.exists(tpath) and B == 65536 and args.ids == "uniform":
+                with open(tpath) as f:
+                    traffic = {k: int(v["traffic_bytes"]) for k, v in json.load(f)["kernels"].items()}
+            for k, v in kernels.items():
+                v["traffic_bytes_ncu"] = traffic.get(k)
             top = max(kernels.items(), key=lambda kv: kv[1]["ms"])
             roof = {"kernel": top[0], "bound": "hbm", "achieved": top[1]["gbs"],
                     "peak": peaks["hbm_gbs"], "unit": "GB/s", "frac": top[1]["frac_hbm"],
-                    "traffic": None, "peak_source": peak_src,
+                    "traffic": traffic.get(top[0]), "peak_source": peak_src,
                     "algorithmic_bytes_per_launch": top[1]["algorithmic_bytes"],
                     "ms_per_launch": top[1]["ms"]}
         cpu = None

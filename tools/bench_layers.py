@@ -72,7 +72,8 @@ def main():
     for B in (1024, 65536):
         fc = [[{"feat": f"I{i}"} for i in range(13)],
               [{"feat": f"C{i}", "feat_num": r, "embed_dim": 8} for i, r in enumerate(rows)]]
-        m = pkg.FMModel(fc, k=8, seed=0)
+        m = pkg.FMModel(fc, k=8, seed=0, sparse_optimizer=pkg.SparseOptimizer("adam"))
+        m.tables.begin_step()
         dense = torch.rand(B, 13, device=dev)
         sparse = torch.stack([torch.randint(0, r, (B,), device=dev) for r in rows], 1).to(torch.int32)
         with torch.no_grad():
@@ -83,7 +84,7 @@ def main():
         g = torch.randn_like(out)
         ms = timed(lambda: out.backward(g, retain_graph=True))
         emit(f"fm_gather_bwd+K2+colsum B={B}", ms, B * (26 * (4 + 2 * kp * 4) + 13 * kp * 4 + kp * 4 + 8),
-             config="FM k=8 (sparse grads, no fused optimizer)")
+             config="FM k=8, fused sparse Adam on the touched rows (K2)")
         del m
     # ---- FM layer as DeepFM calls it
     B = 65536
