@@ -249,6 +249,26 @@ def time_kernels(pkg, model, dev_batches, peaks_gbs):
     return out
 
 
+def count_own_launches(trainer, batch):
+    """Kernels of librtf_b200.so launched by ONE training step on this rank (CUPTI via
+    torch.profiler, on an extra untimed step): the hand-written rtf:: kernels and the tcgen05
+    dense GEMMs instantiated in csrc/dense_gemm_*.cu.  None if the profiler is unavailable."""
+    try:
+        import torch
+        from torch.profiler import ProfilerActivity, profile
+        with profile(activities=[ProfilerActivity.CUDA]) as prof:
+            trainer.step(*batch)
+            torch.cuda.synchronize()
+        n = 0
+        for ev in prof.events():
+            name = ev.name
+            if "rtf::" in name or ("cutlass::device_kernel" in name and "FastF32" in name):
+                n += 1
+        return n or None
+    except Exception:
+        return None
+
+
 CUDA_LIB = "/usr/local/cuda/lib64"
 
 
@@ -382,14 +402,21 @@ def run_b200(args):
         if not args.no_cpu_baseline and world == 1:     # reported on rank 0 at N=1 only
             cpu = cpu_reference_run(args, steps=3, warmup=1)
             cpu = {k: cpu[k] for k in ("value", "unit", "cores", "kind", "sample")}
-        if world == 1:   # fused gather+dot fwd, its bwd, K2 pipeline
-            per_step = 2 + embed_bwd_launches(CRITEO_ROWS, len(CRITEO_ROWS))
-        elif args.exchange == "peer":   # per rank: fused gather+dot fwd/bwd + K2 over the rank's shards
-            mine = [model.layout.local_rows(0, t) for t in model.layout.fields[0]]
-            per_step = (2 + embed_bwd_launches(mine, len(mine))) * world
-        else:            # per rank: K1 + dot-rows fwd/bwd + K2 over the rank's own tables
-            mine = [CRITEO_ROWS[t] for t in model.layout.slots[0]]
-            per_step = (3 + embed_bwd_launches(mine, len(mine))) * world
+        # (one extra step: single-process only — a sharded step is a collective on every rank)
+        per_step = count_own_launches(trainer, dev[W]) if world == 1 else None
+        if per_step is None:   # profiler unavailable: count from the known launch structure
+            if world == 1:     # fused gather+dot fwd, its bwd, K2 pipeline
+                per_step = 2 + embed_bwd_launches(CRITEO_ROWS, len(CRITEO_ROWS))
+            elif args.exchange == "peer":
+                mine = [model.layout.local_rows(0, t) for t in model.layout.fields[0]]
+                per_step = 2 + embed_bwd_launches(mine, len(mine))
+            else:
+                mine = [CRITEO_ROWS[t] for t in model.layout.slots[0]]
+                per_step = 3 + embed_bwd_launches(mine, len(mine))
+            if args.mlp_gemm == "bf16x6":
+                per_step += 7 * 3          # fwd, dgrad, wgrad of the 7 hidden Dense layers
+            per_step += 7 * 2              # fused ReLU-mask + bias-gradient, two stages
+        per_step *= world
         line = {"metric": "dlrm_train_samples_per_sec", "value": B * world * K / (ms_total * 1e-3),
                 "unit": "samples/s", "n_gpus": world, "steps": K, "warmup": W,
                 "ms_per_step": ms_total / K, "higher_is_better": True, "scaling": "weak",
