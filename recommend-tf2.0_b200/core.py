@@ -290,7 +290,8 @@ class _DenseFn(torch.autograd.Function):
             gx = dense_gemm("nt", g, w) if (g.shape[0] >= 1024 and _x6_ok(g, w)) else g @ w.t()
         gw = _wgrad(x, g) if ctx.needs_input_grad[1] else None
         if ctx.kpad:
-            gx = None if gx is None else gx[:, : gx.shape[1] - ctx.kpad]
+            # contiguous: a strided (B, 13) view sends BatchNorm's backward down a 2 ms generic path
+            gx = None if gx is None else gx[:, : gx.shape[1] - ctx.kpad].contiguous()
             gw = None if gw is None else gw[: gw.shape[0] - ctx.kpad]
         return gx, gw, gb, None
 
