@@ -51,6 +51,9 @@ def parse_args():
                          "pulled / gradients pushed over NVLink inside K4; 'p2p' = table-wise, pooled rows "
                          "pulled from the owners' K1 output; 'nccl' = table-wise, NCCL all-to-all")
     ap.add_argument("--row-wise-min-rows", type=int, default=5_000_000)
+    ap.add_argument("--peer-gather", default="owner", choices=["owner", "direct"],
+                    help="peer exchange: rows gathered by their holders (K1) and pulled by sample, or "
+                         "pulled straight from the remote table shards")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-kernel-timing", action="store_true")
     return ap.parse_args()
@@ -143,7 +146,8 @@ def bench_config(args, world):
             "l2_flush": "inputs larger than L2: 17.2 GB of tables, distinct batch every step",
             "parallelism": "single" if world == 1 else
             f"tables sharded over {world} GPUs ({args.exchange} row exchange"
-            + (f", row-wise >= {args.row_wise_min_rows} rows" if args.exchange == "peer" else "")
+            + (f"/{args.peer_gather} gather, row-wise >= {args.row_wise_min_rows} rows"
+               if args.exchange == "peer" else "")
             + ") + dp MLP"}
 
 
@@ -329,7 +333,7 @@ def run_b200(args):
         from recommend_tf2_b200.sharded import PeerShardedDLRM, ShardedDLRM, ShardedDLRMTrainer
         if args.exchange == "peer":
             model = PeerShardedDLRM(fc, BOT_MLP, TOP_MLP, seed=1234, pad_to=args.pad_to,
-                                    row_wise_min_rows=args.row_wise_min_rows)
+                                    row_wise_min_rows=args.row_wise_min_rows, gather=args.peer_gather)
         else:
             model = ShardedDLRM(fc, BOT_MLP, TOP_MLP, seed=1234, pad_to=args.pad_to, exchange=args.exchange)
         trainer = ShardedDLRMTrainer(model, lr=1e-3)
@@ -409,7 +413,7 @@ def run_b200(args):
                 per_step = 2 + embed_bwd_launches(CRITEO_ROWS, len(CRITEO_ROWS))
             elif args.exchange == "peer":
                 mine = [model.layout.local_rows(0, t) for t in model.layout.fields[0]]
-                per_step = 2 + embed_bwd_launches(mine, len(mine))
+                per_step = 2 + (args.peer_gather == "owner") + embed_bwd_launches(mine, len(mine))
             else:
                 mine = [CRITEO_ROWS[t] for t in model.layout.slots[0]]
                 per_step = 3 + embed_bwd_launches(mine, len(mine))

@@ -162,8 +162,12 @@ int rtf_embed_dot_bwd(const float* const* tables, const int64_t* rows, int n_fie
  * there).  d_peer_tab / d_peer_gptr / d_peer_gstr are DEVICE arrays [n_fields][G] (int64):
  * shard base pointers, gradient-column base pointers and per-sample strides.  Bit f of rw_mask:
  * field f is row-wise sharded (row r on rank r % G, local row r / G); otherwise the field lives
- * on one rank and entry [f][0] is used.  rows[] (HOST) = global row counts.                 */
-int rtf_embed_dot_peer_fwd(const int64_t* d_peer_tab, int G, uint64_t rw_mask, const int64_t* rows,
+ * on one rank and entry [f][0] is used.  rows[] (HOST) = global row counts.
+ * d_peer_str != NULL ("owner gather"): the holders ran K1 for the global batch into per-rank
+ * (B_global, T_g*D) buffers; d_peer_tab[f][g] = base of field f's column in rank g's buffer,
+ * d_peer_str[f][g] = its sample stride, and local sample b is read at index sample0 + b.     */
+int rtf_embed_dot_peer_fwd(const int64_t* d_peer_tab, const int64_t* d_peer_str, int64_t sample0,
+                           int G, uint64_t rw_mask, const int64_t* rows,
                            int n_fields, int D, const void* d_ids, int ids_i64, int64_t B,
                            int64_t ids_sb, int64_t ids_sf, const float* d_dense, int64_t dense_sb,
                            float* d_out, int64_t out_sb, int out_cols, float* d_xsave,

@@ -55,7 +55,7 @@ SIGNATURES = {
                           _int, _p, _p],
     "rtf_embed_dot_bwd": [_p, _p, _int, _int, _p, _int, _i64, _i64, _i64, _p, _i64, _p, _i64,
                           _p, _i64, _p, _i64, _p],
-    "rtf_embed_dot_peer_fwd": [_p, _int, C.c_uint64, _p, _int, _int, _p, _int, _i64, _i64, _i64, _p,
+    "rtf_embed_dot_peer_fwd": [_p, _p, _i64, _int, C.c_uint64, _p, _int, _int, _p, _int, _i64, _i64, _i64, _p,
                                _i64, _p, _i64, _int, _p, _i64, _p, _p],
     "rtf_embed_dot_peer_bwd": [_p, _i64, _p, _int, _int, _p, _int, _i64, _i64, _i64, _p, _i64, _p,
                                _i64, _p, _i64, _p, _p, _int, C.c_uint64, _i64, _p],

@@ -473,8 +473,11 @@ class _PeerDotFn(torch.autograd.Function):
         cols = dot_out_cols(F + 1, D, pad_to)
         out = torch.empty((B, cols), dtype=torch.float32, device=dense.device)
         xsave = torch.empty((B, F * D), dtype=torch.float32, device=dense.device)
+        owner = model.gather == "owner"
         rc = L.lib().rtf_embed_dot_peer_fwd(
-            model._d_peer_tab.data_ptr(), lay.world, lay.rw_mask, model._rows_arr, F, D,
+            (model._d_peer_optr if owner else model._d_peer_tab).data_ptr(),
+            model._d_peer_ostr.data_ptr() if owner else None, model.rank * B,
+            lay.world, lay.rw_mask, model._rows_arr, F, D,
             ids.data_ptr(), int(ids.dtype == torch.int64), B, ids.stride(0), ids.stride(1),
             dense.data_ptr(), dense.stride(0), out.data_ptr(), cols, cols, xsave.data_ptr(),
             xsave.stride(0), model.embed_layers.err.data_ptr(), L.current_stream_ptr())
@@ -516,8 +519,18 @@ class PeerShardedDLRM(Layer):
                  top_dnn_hidden_units=(128, 64), activation="relu", dnn_dropout=0.0, embed_reg=1e-4,
                  sparse_optimizer: Optional[SparseOptimizer] = None, pad_to: int = 1,
                  input_bn: bool = True, seed: Optional[int] = None,
-                 row_wise_min_rows: int = 5_000_000, row_wise=None, owners=None):
+                 row_wise_min_rows: int = 5_000_000, row_wise=None, owners=None,
+                 gather: str = "owner"):
+        """gather='owner' (default): every holder runs K1 for the global batch over its shards
+        (a lookup of a row-wise table on the rank that does not hold the row is skipped) into a
+        peer-mapped (B_global, T_g*D) buffer, and K4 pulls each row BY SAMPLE from the holder's
+        buffer — sequential addresses, measured 2.2x faster over NVLink at 8 GPUs than
+        gather='direct', where K4 pulls the random table rows themselves from the remote shards
+        (no K1, no buffer, no id exchange in the forward)."""
         super().__init__()
+        if gather not in ("owner", "direct"):
+            raise ValueError(gather)
+        self.gather = gather
         import torch.distributed._symmetric_memory as symm
         self.world, self.rank = dist.get_world_size(), dist.get_rank()
         self.dense_feature_columns, self.sparse_feature_columns = feature_columns
@@ -564,6 +577,13 @@ class PeerShardedDLRM(Layer):
         self._d_peer_tab = torch.tensor(tab, dtype=torch.int64, device=dev)
         self._d_peer_gptr = torch.tensor(gptr, dtype=torch.int64, device=dev)
         self._d_peer_gstr = torch.tensor(gstr, dtype=torch.int64, device=dev)
+        if self.gather == "owner":      # K1 output of every holder, same layout as the gradients
+            self._out_buf = symm.empty(n, dtype=torch.float32, device=dev)
+            self._out_hdl = symm.rendezvous(self._out_buf, dist.group.WORLD)
+            _, optr, ostr = lay.peer_pointer_tables(self._tab_hdl.buffer_ptrs,
+                                                    self._out_hdl.buffer_ptrs, D)
+            self._d_peer_optr = torch.tensor(optr, dtype=torch.int64, device=dev)
+            self._d_peer_ostr = torch.tensor(ostr, dtype=torch.int64, device=dev)
         self._grad_B = B_local
 
     def call(self, inputs, **kwargs):
@@ -571,15 +591,26 @@ class PeerShardedDLRM(Layer):
         B_local = sparse_inputs.shape[0]
         self._ensure_grad_buffer(B_local)
         train = torch.is_grad_enabled() and self.embed_layers.optimizer is not None
-        if train:
-            # K2 runs where the rows live: every rank needs the ids of the global batch for its
-            # shards (104 B/sample).  Keys, sort and segments start now on a side stream.
+        owner = self.gather == "owner"
+        if train or owner:
+            # the holders need the ids of the global batch for their shards (104 B/sample): K1 in
+            # owner mode, and K2 — whose keys, sort and segments start now on a side stream
             ids_global = exchange_ids(sparse_inputs, self.world)
             loc = local_shard_ids(ids_global, self.layout, self.rank)
-            self._prepared = self.embed_layers.prepare_backward(loc, list(range(loc.shape[1])))
+            if train:
+                self._prepared = self.embed_layers.prepare_backward(loc, list(range(loc.shape[1])))
+        if owner:
+            Tme = loc.shape[1]
+            Bg = B_local * self.world
+            if not train:       # no backward barrier between two forwards: peers may still be
+                self._out_hdl.barrier(channel=1)     # reading the previous batch's rows
+            out_view = self._out_buf[: Bg * Tme * self.D].view(Bg, Tme * self.D)
+            with torch.no_grad():   # foreign lookups of row-wise tables (-1) are skipped silently
+                embed_fwd(list(self.embed_layers.weights), loc, "BF", None, err=None, out=out_view)
         dense_fea = self.bot_dnn(dense_inputs)
-        # every rank's row updates of the previous step are complete before anyone pulls rows
-        self._tab_hdl.barrier(channel=0)
+        # owner: every holder's rows are in place; direct: every rank's row updates of the previous
+        # step are complete before anyone pulls from the tables
+        (self._out_hdl if owner else self._tab_hdl).barrier(channel=0)
         x = _PeerDotFn.apply(self, sparse_inputs, dense_fea, self.pad_to)
         return torch.sigmoid(self.final_dense(self.top_dnn(x)))
 

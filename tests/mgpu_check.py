@@ -24,7 +24,8 @@ def main():
     mode = os.environ.get("RTF_EXCHANGE", "peer")
     single = pkg.DLRM(fc, seed=5, **kw)
     if mode == "peer":   # tables with >= 200 rows are split row-wise, the rest placed table-wise
-        sharded = PeerShardedDLRM(fc, seed=5, row_wise_min_rows=200, **kw)
+        sharded = PeerShardedDLRM(fc, seed=5, row_wise_min_rows=200,
+                                  gather=os.environ.get("RTF_PEER_GATHER", "owner"), **kw)
         lay = sharded.layout
         assert any(lay.row_wise) and not all(lay.row_wise)
         mine = lay.fields[rank]
@@ -74,7 +75,8 @@ def main():
     sharded.embed_layers.check_ids()
     dist.barrier()
     if rank == 0:
-        print(f"mgpu_check ok: world={world} exchange={mode} owners={sharded.layout.owners}"
+        print(f"mgpu_check ok: world={world} exchange={mode}"
+              + (f"/{sharded.gather}" if mode == "peer" else "") + f" owners={sharded.layout.owners}"
               + (f" row_wise={[t for t in range(F) if sharded.layout.row_wise[t]]}" if mode == "peer" else ""))
     dist.destroy_process_group()
 

@@ -10,7 +10,7 @@ pytestmark = pytest.mark.gpu
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
 
-@pytest.mark.parametrize("mode", ["peer", "p2p", "nccl"])
+@pytest.mark.parametrize("mode", ["peer/owner", "peer/direct", "p2p", "nccl"])
 def test_sharded_dlrm_matches_single_gpu(rtf, mode):
     n = torch.cuda.device_count()
     if n < 2:
@@ -19,5 +19,6 @@ def test_sharded_dlrm_matches_single_gpu(rtf, mode):
            "--master-addr", "127.0.0.1", "--master-port", "29711",
            os.path.join(ROOT, "tests", "mgpu_check.py")]
     res = subprocess.run(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True, timeout=600,
-                         env=dict(os.environ, RTF_EXCHANGE=mode))
+                         env=dict(os.environ, RTF_EXCHANGE=mode.split("/")[0],
+                                  RTF_PEER_GATHER=mode.split("/")[-1]))
     assert res.returncode == 0 and "mgpu_check ok" in res.stdout, res.stdout[-3000:]
