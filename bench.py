@@ -79,46 +79,61 @@ def make_batches(n, B, rows, ids_kind, seed):
 
 
 class ClockSampler:
-    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+    """nvidia-smi clocks / throttle reasons sampled every 50 ms from before the warm-up (the tool
+    needs ~0.2 s to start) to the end of the timed region; the summary uses the samples whose
+    timestamps fall inside the timed region, or — when the region is shorter than the sampling
+    period — all samples taken under load (warm-up + timed), and says which."""
+    Q = ("timestamp,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
          "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
          "clocks_event_reasons.sw_power_cap")
 
     def __init__(self, gpu_index):
         self.proc = None
+        self.t_load = time.time()
         try:
             self.proc = subprocess.Popen(
-                ["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "100",
+                ["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "50",
                  "-i", str(gpu_index)], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
         except OSError:
             pass
 
-    def stop(self):
+    def stop(self, t0=None, t1=None):
+        import datetime
         if self.proc is None:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
-        time.sleep(0.15)
+        time.sleep(0.12)
         self.proc.terminate()
         try:
             out, _ = self.proc.communicate(timeout=5)
         except subprocess.TimeoutExpired:
             self.proc.kill()
             out, _ = self.proc.communicate()
-        sm, mx, reasons = [], [], set()
         names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        rows = []
         for line in out.splitlines():
             parts = [p.strip() for p in line.split(",")]
-            if len(parts) < 7:
+            if len(parts) < 8:
                 continue
             try:
-                sm.append(float(parts[0]))
-                mx.append(float(parts[1]))
+                sm_mhz, sm_max = float(parts[1]), float(parts[2])
             except ValueError:
                 continue
-            for nm, v in zip(names, parts[3:7]):
-                if v.lower().startswith("active"):
-                    reasons.add(nm)
+            try:
+                ts = datetime.datetime.strptime(parts[0], "%Y/%m/%d %H:%M:%S.%f").timestamp()
+            except ValueError:
+                ts = float("inf")      # unknown format: counts as "under load", never as "inside"
+            rows.append((ts, sm_mhz, sm_max,
+                         [nm for nm, v in zip(names, parts[4:8]) if v.lower().startswith("active")]))
+        inside = [r for r in rows if t0 is not None and t0 <= r[0] <= t1]
+        window = "timed region"
+        if not inside:
+            inside = [r for r in rows if r[0] >= self.t_load + 0.05] or rows
+            window = "warm-up + timed region (timed region shorter than the sampling period)"
+        sm = [r[1] for r in inside]
         return {"sm_mhz": statistics.median(sm) if sm else None,
-                "sm_max_mhz": max(mx) if mx else None, "reasons": sorted(reasons),
-                "samples": len(sm)}
+                "sm_max_mhz": max(r[2] for r in inside) if inside else None,
+                "reasons": sorted({x for r in inside for x in r[3]}), "samples": len(sm),
+                "window": window}
 
 
 def cpu_reference_run(args, steps, warmup):
@@ -349,18 +364,20 @@ def run_b200(args):
         torch.cuda.synchronize()
 
     # ---- device-resident timing (value)
+    sampler = ClockSampler(local_rank) if rank == 0 else None
     for i in range(W):
         trainer.step(*dev[i])
     barrier()
-    sampler = ClockSampler(local_rank) if rank == 0 else None
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    t_start = time.time()
     e0.record()
     for i in range(W, W + K):
         trainer.step(*dev[i])
     e1.record()
     barrier()
+    t_end = time.time()
     ms_total = e0.elapsed_time(e1)
-    clocks = sampler.stop() if sampler else None
+    clocks = sampler.stop(t_start, t_end) if sampler else None
 
     # ---- end to end: pinned host batches in, loss out, every step, inside the timed region
     loss_host = torch.zeros(K, dtype=torch.float32).pin_memory()

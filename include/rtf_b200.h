@@ -40,7 +40,10 @@ extern "C" {
 #define RTF_E_RANGE (-3)     /* size out of supported range */
 #define RTF_E_WORKSPACE (-4) /* workspace too small */
 
-enum { RTF_POOL_NONE = 0, RTF_POOL_SUM = 1, RTF_POOL_MEAN = 2 };
+enum { RTF_POOL_NONE = 0, RTF_POOL_SUM = 1, RTF_POOL_MEAN = 2,
+       /* OR-ed into rtf_embed_fwd's pool argument (RTF_POOL_NONE only): an out-of-range id leaves its
+        * output row untouched and raises no error flag (owner-gather exchange: foreign lookups) */
+       RTF_POOL_SKIP_INVALID = 0x100 };
 enum { RTF_OPT_NONE = 0, RTF_OPT_SGD = 1, RTF_OPT_ADAGRAD = 2, RTF_OPT_ADAM = 3 };
 
 /* Sparse row-wise optimizer applied in place to the rows touched by a batch.

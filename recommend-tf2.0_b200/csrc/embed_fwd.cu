@@ -22,6 +22,8 @@ struct FwdFields {
   int n_fields;             // fields in this launch
   int field0;               // index of this launch's first field in the full field list
   int sumD;                 // width of one full output row (all fields)
+  int skip_invalid;         // 1: an out-of-range id leaves its output row untouched (no zeros, no
+                            // error flag) — the owner-gather exchange skips foreign lookups this way
 };
 
 // Register cap: with one float4 per lane the kernel is pure latency hiding, so 32 registers
@@ -70,8 +72,8 @@ embed_fwd_vec(const __grid_constant__ FwdFields P, const IdT* __restrict__ ids, 
       nv[u] = 0;
       if (it0 + u < n_items) {
         const long long id = load_id(ids, b * sb + (long long)(P.field0 + f) * sf + l * sl,
-                                     P.rows[f], err);
-        nv[u] = P.dim[f] >> 2;
+                                     P.rows[f], P.skip_invalid ? nullptr : err);
+        nv[u] = (id < 0 && P.skip_invalid) ? 0 : (P.dim[f] >> 2);
         if (id >= 0) src[u] = P.table[f] + id * P.dim[f];
         dst[u] = out + b * out_sb + (long long)l * P.sumD + P.off[f];
         if (++f == F) {
@@ -255,7 +257,10 @@ extern "C" int rtf_embed_fwd(const float* const* tables, const int64_t* rows,
   using namespace rtf;
   if (!tables || !rows || !dims) return RTF_E_ARG;
   if (n_fields <= 0 || B < 0 || L <= 0) return RTF_E_ARG;
+  const int skip_invalid = (pool & RTF_POOL_SKIP_INVALID) ? 1 : 0;
+  pool &= ~RTF_POOL_SKIP_INVALID;
   if (pool < RTF_POOL_NONE || pool > RTF_POOL_MEAN) return RTF_E_ARG;
+  if (skip_invalid && pool != RTF_POOL_NONE) return RTF_E_ARG;
   if (B == 0) return 0;  // empty batch: nothing to read or write
   if (!d_ids || !d_out) return RTF_E_ARG;
   long long sumD = 0;
@@ -274,6 +279,7 @@ extern "C" int rtf_embed_fwd(const float* const* tables, const int64_t* rows,
     P.n_fields = n_fields - f0 < RTF_MAX_FIELDS ? n_fields - f0 : RTF_MAX_FIELDS;
     P.field0 = f0;
     P.sumD = (int)sumD;
+    P.skip_invalid = skip_invalid;
     int dim_max = 0;
     bool vec_ok = ((uintptr_t)d_out % 16 == 0) && (out_sb % 4 == 0) && (sumD % 4 == 0);
     for (int f = 0; f < P.n_fields; ++f) {

@@ -73,9 +73,10 @@ def _ptr_array(tensors: Sequence[Optional[torch.Tensor]]):
 
 def embed_fwd(tables: Sequence[torch.Tensor], ids: torch.Tensor, layout: str = "BF",
               pool: Optional[str] = None, err: Optional[torch.Tensor] = None,
-              out: Optional[torch.Tensor] = None) -> torch.Tensor:
+              out: Optional[torch.Tensor] = None, skip_invalid: bool = False) -> torch.Tensor:
     """K1.  tables[f] is the (rows, dim) fp32 table of lookup field f (a table may repeat).
-    Returns (B, sumD) for L == 1 or pooled lookups, else (B, L, sumD)."""
+    Returns (B, sumD) for L == 1 or pooled lookups, else (B, L, sumD).  skip_invalid: rows of
+    out-of-range ids are left untouched in `out` instead of zero-filled and flagged."""
     lib = L.lib()
     L.require_cuda(ids, "embed_fwd(ids)")
     B, F, Lq, sb, sf, sl = ids_strides(ids, layout)
@@ -89,14 +90,15 @@ def embed_fwd(tables: Sequence[torch.Tensor], ids: torch.Tensor, layout: str = "
     rows = [int(t.shape[0]) for t in tables]
     sumD = sum(dims)
     pm = _POOL[pool]
+    flags = 0x100 if skip_invalid else 0        # RTF_POOL_SKIP_INVALID
     if out is None:
         shape = (B, Lq, sumD) if (pm == L.POOL_NONE and layout != "BF") else (B, sumD)
         out = torch.empty(shape, dtype=torch.float32, device=ids.device)
     out_sb = out.stride(0) if B > 0 else (Lq * sumD)
     rc = lib.rtf_embed_fwd(_ptr_array(tables), L.host_array(C.c_int64, rows),
                            L.host_array(C.c_int32, dims), F, ids.data_ptr(),
-                           int(ids.dtype == torch.int64), B, Lq, sb, sf, sl, pm, out.data_ptr(),
-                           out_sb, None if err is None else err.data_ptr(),
+                           int(ids.dtype == torch.int64), B, Lq, sb, sf, sl, pm | flags,
+                           out.data_ptr(), out_sb, None if err is None else err.data_ptr(),
                            L.current_stream_ptr())
     L.check(rc, "rtf_embed_fwd")
     return out

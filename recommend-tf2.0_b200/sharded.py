@@ -606,7 +606,8 @@ class PeerShardedDLRM(Layer):
                 self._out_hdl.barrier(channel=1)     # reading the previous batch's rows
             out_view = self._out_buf[: Bg * Tme * self.D].view(Bg, Tme * self.D)
             with torch.no_grad():   # foreign lookups of row-wise tables (-1) are skipped silently
-                embed_fwd(list(self.embed_layers.weights), loc, "BF", None, err=None, out=out_view)
+                embed_fwd(list(self.embed_layers.weights), loc, "BF", None, err=None, out=out_view,
+                          skip_invalid=True)
         dense_fea = self.bot_dnn(dense_inputs)
         # owner: every holder's rows are in place; direct: every rank's row updates of the previous
         # step are complete before anyone pulls from the tables

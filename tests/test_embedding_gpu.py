@@ -101,6 +101,27 @@ def test_out_of_range_id_sets_flag_and_reads_zero(rtf):
         ts.check_ids()
 
 
+def test_skip_invalid_leaves_rows_untouched_and_unflagged(rtf):
+    """RTF_POOL_SKIP_INVALID (owner-gather exchange): a lookup with id -1 / >= rows is skipped —
+    its output row keeps what was there, no error flag — the others are gathered bit-exactly."""
+    g = torch.Generator(device="cuda").manual_seed(4)
+    rows, D, B = [50, 7, 1000], 128, 777
+    tabs = [torch.randn(n, D, device="cuda", generator=g) for n in rows]
+    ids = torch.stack([torch.randint(0, n, (B,), device="cuda", generator=g) for n in rows], 1).to(torch.int32)
+    bad = torch.rand(B, 3, device="cuda", generator=g) < 0.4
+    ids_bad = torch.where(bad, torch.full_like(ids, -1), ids)
+    ids_bad[5, 2] = 1000                       # too large counts as invalid as well
+    bad[5, 2] = True
+    err = torch.zeros(1, dtype=torch.int32, device="cuda")
+    out = torch.full((B, 3 * D), 7.25, device="cuda")
+    rtf.embed_fwd(tabs, ids_bad, "BF", None, err=err, out=out, skip_invalid=True)
+    want = torch.cat([t[ids[:, f].long().clamp(0, rows[f] - 1)] for f, t in enumerate(tabs)], 1)
+    keep = bad.repeat_interleave(D, dim=1)
+    assert torch.equal(out[~keep], want[~keep])
+    assert bool((out[keep] == 7.25).all())
+    assert int(err.item()) == 0
+
+
 def test_empty_batch(rtf):
     tab = torch.zeros(10, 8, device="cuda")
     ids = torch.zeros((0, 1), dtype=torch.int32, device="cuda")
