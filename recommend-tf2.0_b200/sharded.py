@@ -354,10 +354,13 @@ class ShardedDLRMTrainer:
         loss = binary_crossentropy(labels, pred)
         self.dense_opt.zero_grad(set_to_none=True)
         (loss / m.world).backward()
-        m.finish_backward()
+        # one flat all-reduce of the MLP gradients, asynchronous so that it overlaps the reverse
+        # exchange barrier + K2 on the embedding shards (finish_backward)
         grads = [p.grad for p in m.dense_parameters() if p.grad is not None]
         flat = torch.cat([g.reshape(-1) for g in grads])
-        dist.all_reduce(flat)
+        work = dist.all_reduce(flat, async_op=True)
+        m.finish_backward()
+        work.wait()
         off = 0
         for g in grads:
             g.copy_(flat[off:off + g.numel()].view_as(g))
