@@ -51,6 +51,9 @@ def parse_args():
                          "pulled / gradients pushed over NVLink inside K4; 'p2p' = table-wise, pooled rows "
                          "pulled from the owners' K1 output; 'nccl' = table-wise, NCCL all-to-all")
     ap.add_argument("--row-wise-min-rows", type=int, default=5_000_000)
+    ap.add_argument("--replicate-max-rows", type=int, default=16384,
+                    help="peer exchange: tables up to this many rows are replicated on every GPU "
+                         "(local lookups, one dense gradient all-reduce); 0 = shard everything")
     ap.add_argument("--peer-gather", default="owner", choices=["owner", "direct"],
                     help="peer exchange: rows gathered by their holders (K1) and pulled by sample, or "
                          "pulled straight from the remote table shards")
@@ -161,8 +164,8 @@ def bench_config(args, world):
             "l2_flush": "inputs larger than L2: 17.2 GB of tables, distinct batch every step",
             "parallelism": "single" if world == 1 else
             f"tables sharded over {world} GPUs ({args.exchange} row exchange"
-            + (f"/{args.peer_gather} gather, row-wise >= {args.row_wise_min_rows} rows"
-               if args.exchange == "peer" else "")
+            + (f"/{args.peer_gather} gather, row-wise >= {args.row_wise_min_rows} rows, "
+               f"replicated <= {args.replicate_max_rows} rows" if args.exchange == "peer" else "")
             + ") + dp MLP"}
 
 
@@ -348,7 +351,8 @@ def run_b200(args):
         from recommend_tf2_b200.sharded import PeerShardedDLRM, ShardedDLRM, ShardedDLRMTrainer
         if args.exchange == "peer":
             model = PeerShardedDLRM(fc, BOT_MLP, TOP_MLP, seed=1234, pad_to=args.pad_to,
-                                    row_wise_min_rows=args.row_wise_min_rows, gather=args.peer_gather)
+                                    row_wise_min_rows=args.row_wise_min_rows, gather=args.peer_gather,
+                                    replicate_max_rows=args.replicate_max_rows)
         else:
             model = ShardedDLRM(fc, BOT_MLP, TOP_MLP, seed=1234, pad_to=args.pad_to, exchange=args.exchange)
         trainer = ShardedDLRMTrainer(model, lr=1e-3)
@@ -429,8 +433,12 @@ def run_b200(args):
             if world == 1:     # fused gather+dot fwd, its bwd, K2 pipeline
                 per_step = 2 + embed_bwd_launches(CRITEO_ROWS, len(CRITEO_ROWS))
             elif args.exchange == "peer":
-                mine = [model.layout.local_rows(0, t) for t in model.layout.fields[0]]
-                per_step = 2 + (args.peer_gather == "owner") + embed_bwd_launches(mine, len(mine))
+                lay = model.layout
+                mine = [lay.local_rows(0, t) for t in lay.shard_fields[0]]
+                per_step = 2 + (args.peer_gather == "owner") + embed_bwd_launches(mine, max(len(mine), 1))
+                if lay.rep_fields:       # replicated tables: local K1 + reduce-only K2
+                    rep = [lay.rows[t] for t in lay.rep_fields]
+                    per_step += 1 + embed_bwd_launches(rep, len(rep))
             else:
                 mine = [CRITEO_ROWS[t] for t in model.layout.slots[0]]
                 per_step = 3 + embed_bwd_launches(mine, len(mine))

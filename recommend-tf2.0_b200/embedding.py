@@ -107,10 +107,13 @@ def embed_fwd(tables: Sequence[torch.Tensor], ids: torch.Tensor, layout: str = "
 def embed_bwd(weights: Sequence[torch.Tensor], field_table: Sequence[int], ids: torch.Tensor,
               grad: torch.Tensor, layout: str = "BF", pool: Optional[str] = None,
               opt: Optional[L.rtf_opt] = None, state1: Optional[Sequence[torch.Tensor]] = None,
-              state2: Optional[Sequence[torch.Tensor]] = None, want_unique: bool = False):
+              state2: Optional[Sequence[torch.Tensor]] = None, want_unique: bool = False,
+              sync: bool = True):
     """K2.  Sorts the (table, id) keys of the batch, sums every touched row's gradient in
     ascending lookup position and applies `opt` in place.  With want_unique=True also returns
-    (keys uint32 as int64 tensor, summed grads (n_unique, dim_max), row_bits)."""
+    (keys uint32 as int64 tensor, summed grads (n_unique, dim_max), row_bits); with sync=False
+    the host is not synchronised: the arrays come back full-size (min(lookups, total rows)
+    entries, unused keys = 0xFFFFFFFF) together with the device-side count."""
     lib = L.lib()
     L.require_cuda(ids, "embed_bwd(ids)")
     L.require_cuda(grad, "embed_bwd(grad)")
@@ -129,8 +132,9 @@ def embed_bwd(weights: Sequence[torch.Tensor], field_table: Sequence[int], ids: 
     ws = torch.empty(max(nbytes.value, 16), dtype=torch.uint8, device=ids.device)
     uk = ug = nu = None
     if want_unique:
-        uk = torch.zeros(max(n, 1), dtype=torch.int32, device=ids.device)
-        ug = torch.zeros((max(n, 1), dim_max), dtype=torch.float32, device=ids.device)
+        cap = max(n, 1) if sync else max(min(n, sum(rows)), 1)
+        uk = torch.full((cap,), 0 if sync else -1, dtype=torch.int32, device=ids.device)
+        ug = torch.zeros((cap, dim_max), dtype=torch.float32, device=ids.device)
         nu = torch.zeros(1, dtype=torch.int32, device=ids.device)
     if opt is None:
         opt = L.rtf_opt(L.OPT_NONE, 0.0, 0.0, 0.0, 0.0, 0.0)
@@ -148,6 +152,8 @@ def embed_bwd(weights: Sequence[torch.Tensor], field_table: Sequence[int], ids: 
                            None if nu is None else nu.data_ptr(), C.byref(row_bits),
                            ws.data_ptr(), ws.numel(), L.current_stream_ptr())
     L.check(rc, "rtf_embed_bwd")
+    if want_unique and not sync:
+        return uk.to(torch.int64) & 0xFFFFFFFF, ug, row_bits.value, nu
     if want_unique:
         k = int(nu.item())
         keys = uk[:k].to(torch.int64) & 0xFFFFFFFF

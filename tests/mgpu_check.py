@@ -24,10 +24,13 @@ def main():
     mode = os.environ.get("RTF_EXCHANGE", "peer")
     single = pkg.DLRM(fc, seed=5, **kw)
     if mode == "peer":   # tables with >= 200 rows are split row-wise, the rest placed table-wise
+        # rows >= 200: row-wise; rows <= RTF_REPLICATE (default 70: 4 tables): replicated; else table-wise
         sharded = PeerShardedDLRM(fc, seed=5, row_wise_min_rows=200,
-                                  gather=os.environ.get("RTF_PEER_GATHER", "owner"), **kw)
+                                  gather=os.environ.get("RTF_PEER_GATHER", "owner"),
+                                  replicate_max_rows=int(os.environ.get("RTF_REPLICATE", "70")), **kw)
         lay = sharded.layout
         assert any(lay.row_wise) and not all(lay.row_wise)
+        assert sum(lay.replicated) == sum(r <= int(os.environ.get("RTF_REPLICATE", "70")) for r in rows)
         mine = lay.fields[rank]
 
         def shard_of(w, t):
@@ -77,7 +80,8 @@ def main():
     if rank == 0:
         print(f"mgpu_check ok: world={world} exchange={mode}"
               + (f"/{sharded.gather}" if mode == "peer" else "") + f" owners={sharded.layout.owners}"
-              + (f" row_wise={[t for t in range(F) if sharded.layout.row_wise[t]]}" if mode == "peer" else ""))
+              + (f" row_wise={[t for t in range(F) if sharded.layout.row_wise[t]]}"
+                 f" replicated={sharded.layout.rep_fields}" if mode == "peer" else ""))
     dist.destroy_process_group()
 
 

@@ -156,3 +156,37 @@ def test_local_shard_ids_partition_every_lookup_once(world):
     want[3, 1] = 0
     want[5, 3] = 0
     assert torch.equal(hits, want)
+
+
+@pytest.mark.parametrize("world", [2, 8])
+def test_peer_layout_replicates_small_tables(world):
+    lay = PeerLayout(CRITEO, [128] * 26, world, replicate_max_rows=16384)
+    rep = [t for t in range(26) if CRITEO[t] <= 16384]
+    assert lay.rep_fields == rep and len(rep) == 18
+    assert sum(CRITEO[t] for t in rep) == 47398          # 24 MB of rows to all-reduce per step
+    for g in range(world):
+        f = lay.fields[g]
+        assert f[len(lay.shard_fields[g]):] == rep        # replicated tables come last, on every rank
+        assert not set(lay.shard_fields[g]) & set(rep)
+        # the replicated shards are contiguous at the end of the rank's table buffer
+        off, total = lay.shard_offsets(g)
+        o = off[rep[0]]
+        for t in rep:
+            assert off[t] == o
+            o += CRITEO[t] * 128
+        assert o == total
+    shard_tables = sorted({t for g in range(world) for t in lay.shard_fields[g]})
+    assert shard_tables == [t for t in range(26) if t not in rep]
+    assert [t for t in range(26) if lay.row_wise[t]] == [t for t in range(26) if CRITEO[t] >= 5_000_000]
+    # pointer tables: a replicated field points at the asking rank's own copy / buffer
+    tab_ptrs = [(g + 1) << 40 for g in range(world)]
+    grad_ptrs = [(g + 101) << 40 for g in range(world)]
+    for me in (0, world - 1):
+        tab, gptr, gstr = lay.peer_pointer_tables(tab_ptrs, grad_ptrs, 128, rank=me)
+        for t in rep:
+            assert tab[t][0] >> 40 == me + 1 and gptr[t][0] >> 40 == me + 101
+            assert gstr[t][0] == len(lay.fields[me]) * 128
+    # ids handed to the holders cover the sharded tables only
+    ids = torch.stack([torch.randint(0, r, (64,)) for r in CRITEO], 1).to(torch.int32)
+    loc = local_shard_ids(ids, lay, 0)
+    assert loc.shape == (64, len(lay.shard_fields[0]))

@@ -20,6 +20,7 @@ from recommend_tf2_b200.sharded import PeerShardedDLRM, ShardedDLRM, ShardedDLRM
 ap = argparse.ArgumentParser()
 ap.add_argument("--exchange", default="peer")
 ap.add_argument("--peer-gather", default="owner")
+ap.add_argument("--replicate-max-rows", type=int, default=16384)
 ap.add_argument("--batch", type=int, default=65536)
 ap.add_argument("--steps", type=int, default=8)
 a = ap.parse_args()
@@ -30,7 +31,8 @@ dist.init_process_group("nccl", device_id=torch.device("cuda", lr))
 torch.backends.cuda.matmul.allow_tf32 = False
 fc = pkg.criteo_feature_columns(bench.EMBED_DIM, rows=bench.CRITEO_ROWS)
 if a.exchange == "peer":
-    m = PeerShardedDLRM(fc, bench.BOT_MLP, bench.TOP_MLP, seed=1, pad_to=8, gather=a.peer_gather)
+    m = PeerShardedDLRM(fc, bench.BOT_MLP, bench.TOP_MLP, seed=1, pad_to=8, gather=a.peer_gather,
+                        replicate_max_rows=a.replicate_max_rows)
 else:
     m = ShardedDLRM(fc, bench.BOT_MLP, bench.TOP_MLP, seed=1, pad_to=8, exchange=a.exchange)
 tr = ShardedDLRMTrainer(m, lr=1e-3)
