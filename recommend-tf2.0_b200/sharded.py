@@ -30,7 +30,7 @@ import torch.distributed as dist
 
 from . import _lib as L
 from .core import DNN, Dense, Layer, binary_crossentropy
-from .embedding import EmbeddingTables, SparseOptimizer, embed_fwd
+from .embedding import EmbeddingTables, SparseOptimizer, embed_bwd, embed_fwd
 from .interaction import dot_out_cols
 
 
