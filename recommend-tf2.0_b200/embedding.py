@@ -266,10 +266,16 @@ class EmbeddingTables(torch.nn.Module):
         ids.record_stream(side)
         return {"ws": ws, "ev": ev, "B": B, "F": F, "L": Lq, "field_table": tuple(field_table)}
 
-    def apply_prepared(self, h, grad, pool=None):
+    def apply_prepared(self, h, grad, pool=None, reduce_only=None):
+        """Gradient half of K2 for a batch prepared by prepare_backward.  reduce_only=(keys int32
+        (cap,), sums (cap, dim_max)): no optimizer — the touched rows' keys and summed gradients
+        are written there instead (cap >= number of touched rows; unused keys keep their value)."""
         lib = L.lib()
         opt = self.optimizer
-        st = opt.struct_for_step(max(opt.step, 1))
+        if reduce_only is not None:
+            st = L.rtf_opt(L.OPT_NONE, 0.0, 0.0, 0.0, 0.0, 0.0)
+        else:
+            st = opt.struct_for_step(max(opt.step, 1))
         rows = [int(w.shape[0]) for w in self.weights]
         dims = [int(w.shape[1]) for w in self.weights]
         torch.cuda.current_stream().wait_event(h["ev"])
@@ -278,8 +284,10 @@ class EmbeddingTables(torch.nn.Module):
                                      L.host_array(C.c_int32, dims), len(rows),
                                      L.host_array(C.c_int32, list(h["field_table"])), h["F"], h["B"],
                                      h["L"], _POOL[pool], grad.data_ptr(), grad.stride(0),
-                                     C.byref(st), None, None, h["ws"].data_ptr(), h["ws"].numel(),
-                                     L.current_stream_ptr())
+                                     C.byref(st),
+                                     None if reduce_only is None else reduce_only[0].data_ptr(),
+                                     None if reduce_only is None else reduce_only[1].data_ptr(),
+                                     h["ws"].data_ptr(), h["ws"].numel(), L.current_stream_ptr())
         L.check(rc, "rtf_embed_bwd_apply")
 
     def apply_sparse_grad(self, ids, field_table, grad, layout="BF", pool=None):

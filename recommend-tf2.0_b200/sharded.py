@@ -639,6 +639,9 @@ class PeerShardedDLRM(Layer):
         if self._Tr:
             ids_rep = sparse_inputs.index_select(1, self._rep_idx).contiguous()   # my samples only
             self._saved_rep_ids = ids_rep
+            if train:   # keys / sort / segments of the replicated lookups: side stream as well
+                self._prepared_rep = self.embed_layers.prepare_backward(
+                    ids_rep, [self._Ts + j for j in range(self._Tr)])
         if owner:
             Tme = self._Ts + self._Tr
             Bg = B_local * self.world
@@ -681,11 +684,16 @@ class PeerShardedDLRM(Layer):
     def _reduce_replicated(self, g_rep):
         """K2 without optimizer over my samples' lookups of the replicated tables -> dense
         (rows, D) gradient block + touched mask, summed over ranks by an asynchronous all-reduce."""
-        Tr, D, R = self._Tr, self.D, self._rep_total
-        W = [w.data for w in list(self.embed_layers.weights)[self._Ts:]]
-        keys, sums, row_bits, _n = embed_bwd(W, list(range(Tr)), self._saved_rep_ids, g_rep, "BF",
-                                             None, want_unique=True, sync=False)
-        tab = keys >> row_bits
+        Tr, Ts, D, R = self._Tr, self._Ts, self.D, self._rep_total
+        cap = min(self._saved_rep_ids.numel(), R) + 1
+        uk = torch.full((cap,), -1, dtype=torch.int32, device=g_rep.device)
+        sums = torch.zeros((cap, D), dtype=torch.float32, device=g_rep.device)
+        self.embed_layers.apply_prepared(self._prepared_rep, g_rep, reduce_only=(uk, sums))
+        keys = uk.to(torch.int64) & 0xFFFFFFFF
+        rows_all = [int(w.shape[0]) for w in self.embed_layers.weights]
+        row_bits = max(1, (max(rows_all) - 1).bit_length())       # K2's key layout: table << row_bits | id
+        tab = (keys >> row_bits) - Ts                             # index among the replicated tables
+        tab = torch.where(tab < 0, torch.full_like(tab, Tr), tab)
         ok = tab < Tr                                             # unused slots hold 0xFFFFFFFF
         idx = torch.where(ok, self._rep_off[tab.clamp(max=Tr)] + (keys & ((1 << row_bits) - 1)),
                           torch.full_like(keys, R))               # -> dummy row R
