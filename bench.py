@@ -328,8 +328,6 @@ def run_b200(args):
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
-    if args.replicate_max_rows < 0:
-        args.replicate_max_rows = 16384 if world >= 4 else 0
     if not torch.cuda.is_available():
         raise SystemExit("bench.py: no CUDA device — the B200 path has no CPU fallback "
                          "(use --impl reference for the host baseline)")
@@ -469,6 +467,9 @@ def run_b200(args):
 
 def main():
     args = parse_args()
+    if args.replicate_max_rows < 0:     # same resolved config for both arms
+        world = int(os.environ.get("WORLD_SIZE", str(args.gpus)))
+        args.replicate_max_rows = 16384 if world >= 4 else 0
     if args.impl == "reference":
         run_reference(args)
     else:
