@@ -352,9 +352,14 @@ def run_b200(args):
     else:
         from recommend_tf2_b200.sharded import PeerShardedDLRM, ShardedDLRM, ShardedDLRMTrainer
         if args.exchange == "peer":
-            model = PeerShardedDLRM(fc, BOT_MLP, TOP_MLP, seed=1234, pad_to=args.pad_to,
-                                    row_wise_min_rows=args.row_wise_min_rows, gather=args.peer_gather,
-                                    replicate_max_rows=args.replicate_max_rows)
+            try:
+                model = PeerShardedDLRM(fc, BOT_MLP, TOP_MLP, seed=1234, pad_to=args.pad_to,
+                                        row_wise_min_rows=args.row_wise_min_rows, gather=args.peer_gather,
+                                        replicate_max_rows=args.replicate_max_rows)
+            except Exception as e:   # no NVLink peer mapping on this box: NCCL all-to-all, table-wise
+                sys.stderr.write(f"bench.py: peer exchange unavailable ({e!r}); using --exchange nccl\n")
+                args.exchange = "nccl"
+                model = ShardedDLRM(fc, BOT_MLP, TOP_MLP, seed=1234, pad_to=args.pad_to, exchange="nccl")
         else:
             model = ShardedDLRM(fc, BOT_MLP, TOP_MLP, seed=1234, pad_to=args.pad_to, exchange=args.exchange)
         trainer = ShardedDLRMTrainer(model, lr=1e-3)
