@@ -54,7 +54,7 @@ template <class LayoutA, class LayoutB, int Bands, class MmaTile = Shape<_256, _
           class Cluster = Shape<_2, _1, _1>,
           class MainSchedule = cutlass::gemm::KernelTmaWarpSpecialized2SmFastFP32SmemSm100,
           class EpiSchedule = cutlass::epilogue::TmaWarpSpecialized2Sm, class ElementC = void,
-          int PromotionInterval = 2>
+          int PromotionInterval = 2, class AccCopyAtom = void>
 struct FastF32Gemm {
   using Arch = cutlass::arch::Sm100;
   using OpClass = cutlass::arch::OpClassTensorOp;
@@ -74,7 +74,8 @@ struct FastF32Gemm {
       SP::Schedule::SchedulerPipelineStageCount, SP::Schedule::AccumulatorPipelineStageCount, Bands,
       SP::ScalingFactor, (PromotionInterval > 0 ? PromotionInterval : SP::AccPromotionInterval),
       typename SP::ClusterShape,
-      typename SP::AccumulatorCopyAtom, typename SP::ArchTag>;
+      cute::conditional_t<cute::is_void_v<AccCopyAtom>, typename SP::AccumulatorCopyAtom, AccCopyAtom>,
+      typename SP::ArchTag>;
   using Mainloop = cutlass::gemm::collective::CollectiveMma<
       Policy, typename Stock::TileShape, float, typename Stock::StrideA, float,
       typename Stock::StrideB, typename Stock::TiledMma, typename Stock::GmemTiledCopyA,
