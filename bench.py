@@ -205,20 +205,22 @@ def time_kernels(pkg, model, dev_batches, peaks_gbs):
     cols = pkg.dot_out_cols(F + 1, D, model.pad_to)
     res = {}
 
-    def timed(fn, n):
+    def timed(fn, n, warm=3):
+        for i in range(warm):          # untimed: clocks, caches and lazy inits settle per kernel
+            fn(i % n)
         torch.cuda.synchronize()
         evs = []
         for i in range(n):
             a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
             # keep the stream busy while the host enqueues, so the events bracket device time
             # only (not the Python/ctypes launch latency of an idle stream)
-            torch.cuda._sleep(400_000)
+            torch.cuda._sleep(600_000)
             a.record()
             fn(i)
             b.record()
             evs.append((a, b))
         torch.cuda.synchronize()
-        return statistics.mean(a.elapsed_time(b) for a, b in evs)
+        return statistics.median(a.elapsed_time(b) for a, b in evs)
 
     n = len(dev_batches)
     B = dev_batches[0][1].shape[0]
