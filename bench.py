@@ -426,6 +426,10 @@ def run_b200(args):
                     traffic = {k: int(v["traffic_bytes"]) for k, v in json.load(f)["kernels"].items()}
             for k, v in kernels.items():
                 v["traffic_bytes_ncu"] = traffic.get(k)
+                # DRAM-side rate: tables smaller than L2 (11 of the 26) are served from L2, so the
+                # algorithmic rate of a gather can exceed the HBM peak while the DRAM rate does not
+                v["dram_gbs_ncu_traffic"] = (round(traffic[k] / (v["ms"] * 1e-3) / 1e9, 1)
+                                             if k in traffic else None)
             top = max(kernels.items(), key=lambda kv: kv[1]["ms"])
             roof = {"kernel": top[0], "bound": "hbm", "achieved": top[1]["gbs"],
                     "peak": peaks["hbm_gbs"], "unit": "GB/s", "frac": top[1]["frac_hbm"],
