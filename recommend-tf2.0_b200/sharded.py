@@ -2,23 +2,32 @@
 
 The reference only knows tf.distribute.MirroredStrategy: every table is replicated and, being
 l2-regularised, its dense gradient is all-reduced every step (src/ctr/fm/train.py:43-50).
-Here each table lives on ONE rank (table-wise sharding, greedy balance of lookup count then
-bytes); the dense MLPs stay data-parallel.  One process per GPU, torch.distributed (NCCL over
-NVLink) for the plumbing:
+Here the dense MLPs stay data-parallel and the tables are placed per size; one process per GPU,
+torch.distributed (NCCL over NVLink) for the plumbing.  Two implementations:
 
-  forward   ids (B_local,F) --all-gather--> (B_global,F)
-            K1 on the owner: local tables x global batch          -> (B_global, T_me*D)
-            all-to-all of pooled rows (async, overlaps the bottom MLP)
-            K4 reads the receive buffer in place (rows addressed by base+stride, blocks ordered
-            by source rank) — interaction output identical to the single-GPU one
-  backward  K4 bwd writes dX rows straight into the send buffer of the reverse all-to-all
-            (async, overlaps the bottom-MLP backward) -> K2 + fused sparse Adam on the owner
-            (no table gradient ever crosses the wire as a dense tensor); MLP grads all-reduce.
+PeerShardedDLRM (default) — three placements chosen per table:
+  row-wise     (>= 5 M rows)   row r on rank r % G at local row r // G
+  table-wise   (the middle)    one owner, greedy balance of lookup count then bytes
+  replicated   (<= 16 K rows)  a copy on every rank; gradients combined by one dense all-reduce
+  forward   all-gather of the ids -> K1 on every holder over the global batch for its shards
+            (foreign lookups of row-wise tables skipped) into a peer-mapped (B_global, T_g*D)
+            buffer; replicated tables gathered locally -> one barrier ->
+            K4 pulls the rows of its local samples from the holders' buffers with TMA bulk
+            copies over NVLink, inside the interaction kernel (no NCCL all-to-all, no staging)
+  backward  K4 bwd stores each dX row straight into the holder's gradient buffer -> barrier ->
+            K2 + fused sparse Adam on the holders (keys/sort on a side stream since the forward);
+            replicated tables: reduce-only K2 per rank + async dense all-reduce + identical row
+            update on every replica; MLP gradients: one flat async all-reduce overlapping K2.
+  gather='direct' instead pulls the random table rows themselves from the remote shards
+  (no K1, no id exchange in the forward; 2.2x slower over NVLink at 8 GPUs).
 
-Row-wise sharding of the >= 5 M-row tables (north star) is the next step: at 180 GB per GPU it
-is a load-balance refinement (26 tables over 8 ranks = 4/3/3/...), not a capacity need.
-The exchange helpers are device-agnostic (gloo on CPU in tests); only lookups/interaction
-need CUDA.
+ShardedDLRM — table-wise only, K1 on owners, then either K4 pulls the pooled rows from the
+owners' output buffers (exchange='p2p') or an async NCCL all-to-all that overlaps the bottom MLP
+(exchange='nccl'); K4 reads the receive buffer in place (rows addressed by base+stride, blocks
+ordered by source rank); reverse exchange symmetric.
+
+The placement / exchange-layout helpers are device-agnostic (gloo on CPU in tests); only
+lookups and the interaction need CUDA.
 """
 from __future__ import annotations
 
