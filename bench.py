@@ -177,7 +177,7 @@ def run_reference(args):
         return
     world = int(os.environ.get("WORLD_SIZE", str(args.gpus)))
     r = cpu_reference_run(args, args.steps, max(args.warmup, 1))
-    line = {"metric": "dlrm_train_samples_per_sec", "value": r["value"], "unit": "samples/s",
+    line = {"metric": "DLRM train samples/sec", "value": r["value"], "unit": "samples/s",
             "impl": "reference", "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": r["ms_per_step"], "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "f32", "data": "synthetic",
@@ -459,7 +459,7 @@ def run_b200(args):
                 per_step += 7 * 3          # fwd, dgrad, wgrad of the 7 hidden Dense layers
             per_step += 7 * 2              # fused ReLU-mask + bias-gradient, two stages
         per_step *= world
-        line = {"metric": "dlrm_train_samples_per_sec", "value": B * world * K / (ms_total * 1e-3),
+        line = {"metric": "DLRM train samples/sec", "value": B * world * K / (ms_total * 1e-3),
                 "unit": "samples/s", "n_gpus": world, "steps": K, "warmup": W,
                 "ms_per_step": ms_total / K, "higher_is_better": True, "scaling": "weak",
                 "vs_baseline": None, "dtype": "f32", "data": "synthetic",
