@@ -108,3 +108,28 @@ def test_dice():
     p = 1 / (1 + np.exp(-(g["x"] / np.sqrt(1 + 1e-3))))
     close(g["alpha"] * (1 - p) * g["x"] + p * g["x"], g["out"])
     assert abs(float(g["alpha"])) <= np.sqrt(3)
+
+
+def test_committed_goldens_are_reproducible_from_the_reference_source(tmp_path):
+    """Where the reference checkout exists (the build container; it does not travel to the GPU
+    box), tools/make_golden.py re-executes the reference's own layer code over the numpy
+    TensorFlow stand-in and must reproduce every committed fixture bit for bit."""
+    import os
+    import subprocess
+    import sys
+    ref = os.environ.get("RTF_REFERENCE", "/root/reference")
+    if not os.path.isdir(os.path.join(ref, "src", "ctr", "layers")):
+        pytest.skip("reference checkout not present")
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    res = subprocess.run([sys.executable, os.path.join(root, "tools", "make_golden.py")],
+                         env=dict(os.environ, RTF_GOLDEN_OUT=str(tmp_path)), stdout=subprocess.PIPE,
+                         stderr=subprocess.STDOUT, text=True, timeout=600)
+    assert res.returncode == 0, res.stdout[-2000:]
+    committed = sorted(f for f in os.listdir(os.path.join(root, "tests", "golden")) if f.endswith(".npz"))
+    assert sorted(os.listdir(tmp_path)) == committed and len(committed) >= 11
+    for f in committed:
+        a = np.load(os.path.join(root, "tests", "golden", f))
+        b = np.load(os.path.join(tmp_path, f))
+        assert sorted(a.files) == sorted(b.files), f
+        for k in a.files:
+            assert np.array_equal(a[k], b[k]), (f, k)

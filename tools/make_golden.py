@@ -21,7 +21,7 @@ sys.path.insert(0, os.path.join(REF, "src"))
 
 import tensorflow as tf  # noqa: E402  (the shim)
 
-OUT = os.path.join(ROOT, "tests", "golden")
+OUT = os.environ.get("RTF_GOLDEN_OUT", os.path.join(ROOT, "tests", "golden"))
 
 
 def save(name, **arrays):
