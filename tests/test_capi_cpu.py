@@ -43,6 +43,15 @@ def test_version_and_arg_errors_without_gpu(built):
     nbytes = ctypes.c_size_t(0)
     assert lib.rtf_embed_bwd_workspace(1 << 20, 128, ctypes.byref(nbytes)) == 0
     assert nbytes.value > (1 << 20) * 16
+    # dense GEMM: NULL operands -> RTF_E_ARG, a leading dimension that breaks the 16-byte rows -> RTF_E_ALIGN
+    for fn in (lib.rtf_dense_gemm_nn, lib.rtf_dense_gemm_nt, lib.rtf_dense_gemm_tn):
+        assert fn(None, 8, 0, None, 8, 0, None, 0, None, 8, 0, 4, 8, 8, 1, None, 0, None) == -1
+        assert fn(0x1000, 6, 0, 0x2000, 8, 0, None, 0, 0x3000, 8, 0, 4, 8, 8, 1, None, 0, None) == -2
+    # peer-memory interaction: missing pointer tables -> RTF_E_ARG
+    assert lib.rtf_embed_dot_peer_fwd(None, None, 0, 2, 0, None, 3, 8, None, 0, 4, 3, 1, None, 8, None, 16,
+                                      16, None, 0, None, None) == -1
+    assert lib.rtf_embed_dot_peer_bwd(None, 0, None, 3, 8, None, 0, 4, 3, 1, None, 8, None, 16, None, 8,
+                                      None, None, 2, 0, 0, None) == -1
 
 
 def test_product_path_has_no_cpu_fallback(built):
