@@ -288,7 +288,8 @@ def count_own_launches(trainer, batch):
         n = 0
         for ev in prof.events():
             name = ev.name
-            if "rtf::" in name or ("cutlass::device_kernel" in name and "FastF32" in name):
+            # (the GEMM's name may come back mangled: _ZN7cutlass13device_kernelI...FastF32...)
+            if "rtf::" in name or "N3rtf" in name or ("device_kernel" in name and "FastF32" in name):
                 n += 1
         return n or None
     except Exception:
