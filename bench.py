@@ -395,6 +395,8 @@ def run_b200(args):
 
     # ---- end to end: pinned host batches in, loss out, every step, inside the timed region
     loss_host = torch.zeros(K, dtype=torch.float32).pin_memory()
+    for _ in pkg.DeviceFeeder(host[:2]):     # untimed: lets the allocator cache the staging slots
+        pass
     barrier()
     f0, f1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     f0.record()
