@@ -479,6 +479,51 @@ def local_shard_ids(ids_global: torch.Tensor, layout: PeerLayout, rank: int) -> 
     return loc.contiguous()
 
 
+def scatter_unique_rows(keys: torch.Tensor, sums: torch.Tensor, row_bits: int, first_table: int,
+                        rep_off: torch.Tensor, R: int, D: int) -> torch.Tensor:
+    """K2's unique-row output of the replicated tables -> dense block.  keys (cap,) int64 =
+    table << row_bits | row (unused slots 0xFFFFFFFF), sums (cap, >= D); tables first_table ..
+    first_table + Tr - 1 are the replicated ones, rep_off (Tr + 1,) their row offsets in the
+    block (last entry = total R, also passed as a host int: no device sync here).  Returns G (R + 1, D + 1): summed gradient per row, column D =
+    1 where the row was touched on this rank; row R collects the unused slots."""
+    Tr = rep_off.numel() - 1
+    tab = (keys >> row_bits) - first_table
+    tab = torch.where(tab < 0, torch.full_like(tab, Tr), tab)
+    ok = tab < Tr
+    idx = torch.where(ok, rep_off[tab.clamp(max=Tr)] + (keys & ((1 << row_bits) - 1)),
+                      torch.full_like(keys, R))
+    G = torch.zeros((R + 1, D + 1), dtype=torch.float32, device=keys.device)
+    G[:, :D].index_copy_(0, idx, sums[:, :D])                 # unique rows (duplicates only at R)
+    G[:, D].index_fill_(0, idx, 1.0)
+    return G
+
+
+def apply_touched_rows(opt: SparseOptimizer, lr_t: float, W: torch.Tensor, m: Optional[torch.Tensor],
+                       v: Optional[torch.Tensor], G: torch.Tensor) -> None:
+    """K2's row update (csrc/embed_bwd.cu finish_row) on a dense block, in place, for the rows
+    whose touched count G[:, D] is > 0: g = sum + 2*l2*w, then SGD / Adagrad / Adam (Keras form,
+    lr_t already carries the bias corrections).  Untouched rows and their state do not move."""
+    R, D = W.shape
+    touched = (G[:R, D] > 0).unsqueeze(1)
+    g = G[:R, :D]
+    if opt.l2 > 0:
+        g = g + (2.0 * opt.l2) * W
+    if opt.kind == "sgd":
+        W.copy_(torch.where(touched, W - lr_t * g, W))
+    elif opt.kind == "adagrad":
+        a = m + g * g
+        W.copy_(torch.where(touched, W - (lr_t * g) / (a.sqrt() + opt.eps), W))
+        m.copy_(torch.where(touched, a, m))
+    elif opt.kind == "adam":
+        m2 = opt.beta1 * m + (1.0 - opt.beta1) * g
+        v2 = opt.beta2 * v + (1.0 - opt.beta2) * (g * g)
+        W.copy_(torch.where(touched, W - (lr_t * m2) / (v2.sqrt() + opt.eps), W))
+        m.copy_(torch.where(touched, m2, m))
+        v.copy_(torch.where(touched, v2, v))
+    else:
+        raise ValueError(opt.kind)
+
+
 class _PeerDotFn(torch.autograd.Function):
     """K1+K4 over tables sharded across the GPUs of the box: the forward's TMA bulk copies pull
     every embedding row from whichever GPU holds it (NVLink peer memory) and keep a local copy
@@ -701,14 +746,7 @@ class PeerShardedDLRM(Layer):
         keys = uk.to(torch.int64) & 0xFFFFFFFF
         rows_all = [int(w.shape[0]) for w in self.embed_layers.weights]
         row_bits = max(1, (max(rows_all) - 1).bit_length())       # K2's key layout: table << row_bits | id
-        tab = (keys >> row_bits) - Ts                             # index among the replicated tables
-        tab = torch.where(tab < 0, torch.full_like(tab, Tr), tab)
-        ok = tab < Tr                                             # unused slots hold 0xFFFFFFFF
-        idx = torch.where(ok, self._rep_off[tab.clamp(max=Tr)] + (keys & ((1 << row_bits) - 1)),
-                          torch.full_like(keys, R))               # -> dummy row R
-        G = torch.zeros((R + 1, D + 1), dtype=torch.float32, device=keys.device)
-        G[:, :D].index_copy_(0, idx, sums[:, :D])                 # unique rows (duplicates only at R)
-        G[:, D].index_fill_(0, idx, 1.0)                          # touched on this rank
+        G = scatter_unique_rows(keys, sums, row_bits, Ts, self._rep_off, R, D)
         work = dist.all_reduce(G, async_op=True)
         return G, work
 
@@ -731,26 +769,7 @@ class PeerShardedDLRM(Layer):
         work.wait()
         opt = tl.optimizer
         st = opt.struct_for_step(max(opt.step, 1))
-        R, D = self._rep_total, self.D
-        touched = (G[:R, D] > 0).unsqueeze(1)
-        W = self._rep_W
-        g = G[:R, :D]
-        if opt.l2 > 0:
-            g = g + (2.0 * opt.l2) * W
-        if opt.kind == "sgd":
-            W.copy_(torch.where(touched, W - st.lr * g, W))
-        elif opt.kind == "adagrad":
-            a = self._rep_m + g * g
-            W.copy_(torch.where(touched, W - (st.lr * g) / (a.sqrt() + opt.eps), W))
-            self._rep_m.copy_(torch.where(touched, a, self._rep_m))
-        elif opt.kind == "adam":
-            m = opt.beta1 * self._rep_m + (1.0 - opt.beta1) * g
-            v = opt.beta2 * self._rep_v + (1.0 - opt.beta2) * (g * g)
-            W.copy_(torch.where(touched, W - (st.lr * m) / (v.sqrt() + opt.eps), W))
-            self._rep_m.copy_(torch.where(touched, m, self._rep_m))
-            self._rep_v.copy_(torch.where(touched, v, self._rep_v))
-        else:
-            raise ValueError(opt.kind)
+        apply_touched_rows(opt, st.lr, self._rep_W, self._rep_m, self._rep_v, G)
 
     def dense_parameters(self):
         emb = {id(p) for p in self.embed_layers.parameters()}

@@ -190,3 +190,73 @@ def test_peer_layout_replicates_small_tables(world):
     ids = torch.stack([torch.randint(0, r, (64,)) for r in CRITEO], 1).to(torch.int32)
     loc = local_shard_ids(ids, lay, 0)
     assert loc.shape == (64, len(lay.shard_fields[0]))
+
+
+# ---- replicated (data-parallel) small tables: dense gradient combine + touched-row update -----
+from recommend_tf2_b200.embedding import SparseOptimizer  # noqa: E402
+from recommend_tf2_b200.sharded import apply_touched_rows, scatter_unique_rows  # noqa: E402
+from oracle import embedding as OE  # noqa: E402
+
+
+def _rep_worker(rank, world, port, kind):
+    """Every rank reduces its own lookups (what K2 emits: sorted unique keys + summed rows),
+    scatters them into the dense block, all-reduces it and updates the rows touched anywhere;
+    the replicas must stay identical and equal the single-process update over the whole batch."""
+    import numpy as np
+    os.environ["MASTER_ADDR"], os.environ["MASTER_PORT"] = "127.0.0.1", str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        rows, D, Ts, B_local = [5, 40, 3], 8, 2, 64          # tables 2..4 replicated; 0..1 sharded
+        R = sum(rows)
+        row_bits = 13                                         # as if a sharded table had 8192 rows
+        rep_off = torch.tensor([0, 5, 45, 48])
+        g = torch.Generator().manual_seed(7)
+        W0 = torch.randn(R, D, generator=g)
+        ids_all = torch.stack([torch.randint(0, r, (B_local * world,), generator=g) for r in rows], 1)
+        grad_all = torch.randn(B_local * world, len(rows), D, generator=g)
+        opt = SparseOptimizer(kind, lr=1e-2, l2=1e-3)
+        # --- this rank: unique (table,row) keys + sums over ITS samples, padded like K2's output
+        sl = slice(rank * B_local, (rank + 1) * B_local)
+        dense = torch.zeros(R, D)
+        for j in range(len(rows)):
+            dense.index_add_(0, rep_off[j] + ids_all[sl, j], grad_all[sl, j])
+        keys = torch.cat([((Ts + j) << row_bits) | torch.unique(ids_all[sl, j]) for j in range(len(rows))])
+        idx = torch.cat([rep_off[j] + torch.unique(ids_all[sl, j]) for j in range(len(rows))])
+        cap = R + 1
+        uk = torch.full((cap,), 0xFFFFFFFF, dtype=torch.int64)
+        uk[: keys.numel()] = keys
+        sums = torch.zeros(cap, D)
+        sums[: keys.numel()] = dense[idx]
+        G = scatter_unique_rows(uk, sums, row_bits, Ts, rep_off, R, D)
+        assert torch.equal(G[:R, :D], dense) and torch.equal(G[:R, D] > 0, dense.abs().sum(1) > 0)
+        dist.all_reduce(G)
+        W, m, v = W0.clone(), torch.zeros(R, D), torch.zeros(R, D)
+        lr_t = opt.struct_for_step(1).lr
+        apply_touched_rows(opt, lr_t, W, m, v, G)
+        # --- reference: the numpy oracle's row update over the union of all ranks' lookups
+        Wn = [W0[rep_off[j]: rep_off[j + 1]].numpy().copy() for j in range(len(rows))]
+        s1 = [np.zeros_like(w) for w in Wn]
+        s2 = [np.zeros_like(w) for w in Wn]
+        full = torch.zeros(R, D)
+        for j in range(len(rows)):
+            full.index_add_(0, rep_off[j] + ids_all[:, j], grad_all[:, j])
+        for j in range(len(rows)):
+            for r in torch.unique(ids_all[:, j]).tolist():
+                OE.sparse_optimizer_step(kind, Wn[j], s1[j], s2[j], r,
+                                         full[rep_off[j] + r].numpy(), lr_t, eps=opt.eps, l2=opt.l2)
+        want = torch.from_numpy(np.concatenate(Wn, 0))
+        torch.testing.assert_close(W, want, rtol=2e-5, atol=1e-6)
+        untouched = torch.ones(R, dtype=torch.bool)
+        for j in range(len(rows)):
+            untouched[rep_off[j] + torch.unique(ids_all[:, j])] = False
+        assert torch.equal(W[untouched], W0[untouched]) and not bool(m[untouched].any())
+        gathered = [torch.empty_like(W) for _ in range(world)]
+        dist.all_gather(gathered, W)
+        assert all(torch.equal(gathered[0], t) for t in gathered)        # replicas stay identical
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("kind", ["adam", "adagrad", "sgd"])
+def test_replicated_tables_combine_and_update_gloo(kind):
+    mp.spawn(_rep_worker, args=(2, _free_port(), kind), nprocs=2, join=True)
