@@ -260,3 +260,46 @@ def _rep_worker(rank, world, port, kind):
 @pytest.mark.parametrize("kind", ["adam", "adagrad", "sgd"])
 def test_replicated_tables_combine_and_update_gloo(kind):
     mp.spawn(_rep_worker, args=(2, _free_port(), kind), nprocs=2, join=True)
+
+
+# ---- property test: any table list / world size gives a consistent placement -------------------
+from hypothesis import given, settings  # noqa: E402
+from hypothesis import strategies as st  # noqa: E402
+
+
+@settings(max_examples=60, deadline=None)
+@given(st.lists(st.integers(1, 3_000_000), min_size=1, max_size=40), st.sampled_from([1, 2, 3, 4, 8]),
+       st.integers(0, 50_000), st.integers(100_000, 2_000_000))
+def test_peer_layout_is_consistent_for_any_tables(rows, world, rep_max, rw_min):
+    D = 16
+    lay = PeerLayout(rows, [D] * len(rows), world, row_wise_min_rows=rw_min, replicate_max_rows=rep_max)
+    n = len(rows)
+    for t in range(n):
+        kinds = [lay.replicated[t], lay.row_wise[t], lay.owners[t] >= 0]
+        assert sum(kinds) == 1                                   # exactly one placement class
+        holders = [g for g in range(world) if t in lay.fields[g]]
+        if lay.replicated[t] or lay.row_wise[t]:
+            assert holders == list(range(world))
+        else:
+            assert holders == [lay.owners[t]]
+        if not lay.replicated[t]:                                # sharded rows add up to the table
+            assert sum(lay.local_rows(g, t) for g in holders) == rows[t]
+    if world == 1:
+        assert not any(lay.replicated) and not any(lay.row_wise)
+    for g in range(world):
+        assert lay.fields[g] == lay.shard_fields[g] + lay.rep_fields
+        off, total = lay.shard_offsets(g)
+        spans = sorted((off[t], off[t] + lay.local_rows(g, t) * D) for t in lay.fields[g])
+        if not spans:                                            # more ranks than tables
+            assert total == 0
+            continue
+        assert spans[0][0] == 0 and spans[-1][1] == total
+        assert all(a[1] == b[0] for a, b in zip(spans, spans[1:]))     # shards tile the buffer
+        assert lay.buffer_elems() >= total
+    # a few random rows: the holder map agrees with the shard sizes
+    for t in range(min(n, 5)):
+        if lay.replicated[t]:
+            continue
+        for r in {0, rows[t] - 1, rows[t] // 2}:
+            g, local = lay.holder(t, r)
+            assert 0 <= g < world and 0 <= local < lay.local_rows(g, t)
