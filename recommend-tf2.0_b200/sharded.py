@@ -401,8 +401,11 @@ class PeerLayout:
         self.world, self.rows, self.dims, self.n_tables = world, list(rows), list(dims), n
         self.replicated = [world > 1 and rows[t] <= replicate_max_rows for t in range(n)]
         if row_wise is None:
-            row_wise = [world > 1 and rows[t] >= row_wise_min_rows for t in range(n)]
+            row_wise = [world > 1 and rows[t] >= max(row_wise_min_rows, world) for t in range(n)]
         self.row_wise = [bool(x) and not self.replicated[t] for t, x in enumerate(row_wise)]
+        for t in range(n):
+            if self.row_wise[t] and rows[t] < world:
+                raise ValueError(f"table {t} has {rows[t]} rows: too few to split over {world} ranks")
         tw = [t for t in range(n) if not self.row_wise[t] and not self.replicated[t]]
         if owners is None:
             own_tw = plan_table_owners([rows[t] for t in tw], [dims[t] for t in tw], world)
