@@ -60,6 +60,8 @@ def parse_args():
                     help="peer exchange: rows gathered by their holders (K1) and pulled by sample, or "
                          "pulled straight from the remote table shards")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-parity-check", action="store_true",
+                    help="skip the untimed sharded-vs-single-GPU self-check run before a multi-GPU measurement")
     ap.add_argument("--no-kernel-timing", action="store_true")
     return ap.parse_args()
 
@@ -171,6 +173,20 @@ def bench_config(args, world):
             + ") + dp MLP"}
 
 
+def reference_config(args):
+    """The config the CPU arm ACTUALLY runs: same model, a bounded batch and tables capped to fit
+    host RAM (the GPU arm's config is repeated under "gpu_arm_config" for the comparison)."""
+    rows = [min(r, args.cpu_row_cap) for r in CRITEO_ROWS]
+    return {"workload": "dlrm_criteo_synthetic", "tables": len(rows), "rows_total": sum(rows),
+            "row_cap": args.cpu_row_cap, "embed_dim": EMBED_DIM, "bot_mlp": list(BOT_MLP),
+            "top_mlp": list(TOP_MLP), "interaction": "dot", "batch_per_gpu": args.cpu_batch,
+            "global_batch": args.cpu_batch, "ids": args.ids,
+            "optimizer": "adam (sparse rows for the tables, dense for the MLP)",
+            "parallelism": "host cores, one process", "same_config": False,
+            "differs_from_gpu_arm": "batch (bounded sample) and table rows capped at row_cap "
+                                    "(host RAM); identical model, dims, id distribution"}
+
+
 def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
@@ -181,7 +197,7 @@ def run_reference(args):
             "impl": "reference", "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": r["ms_per_step"], "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": bench_config(args, world),
+            "config": dict(reference_config(args), gpu_arm_config=bench_config(args, world)),
             "cpu_baseline": {k: r[k] for k in ("value", "unit", "cores", "kind", "sample")},
             "e2e": {"value": r["value"], "unit": "samples/s", "h2d_bytes_per_step": 0,
                     "d2h_bytes_per_step": 0}}
@@ -348,19 +364,39 @@ def run_b200(args):
 
     B = args.batch
     K, W = args.steps, max(args.warmup, 3)
+    parity = None
     fc = pkg.criteo_feature_columns(EMBED_DIM, rows=CRITEO_ROWS)
     if world == 1:
         model = pkg.DLRM(fc, BOT_MLP, TOP_MLP, interaction="dot", seed=1234, pad_to=args.pad_to)
         trainer = pkg.DLRMTrainer(model, lr=1e-3)
     else:
-        from recommend_tf2_b200.sharded import PeerShardedDLRM, ShardedDLRM, ShardedDLRMTrainer
+        from recommend_tf2_b200.sharded import (PeerShardedDLRM, ShardedDLRM, ShardedDLRMTrainer,
+                                                all_ranks_ok, parity_self_check)
+        # untimed: sharded == single-GPU replica on this very world, for the exchange mode measured
+        # (row-wise + table-wise + replicated tables forced; plus the all-sharded placement when
+        # the measured config replicates nothing)
+        if not args.no_parity_check:
+            checks = [parity_self_check(args.exchange, args.peer_gather, 70)]
+            if args.exchange == "peer" and args.replicate_max_rows == 0:
+                checks.append(parity_self_check(args.exchange, args.peer_gather, 0))
+            parity = {"world": world, "modes": [m for c in checks for m in c["modes"]],
+                      "steps": checks[0]["steps"],
+                      "max_rel_err": max(c["max_rel_err"] for c in checks),
+                      "max_rel_err_state": max(c["max_rel_err_state"] for c in checks),
+                      "tol": 1e-5, "tol_state": 1e-4, "ok": all(c["ok"] for c in checks),
+                      "what": "sharded vs single-GPU replica on every rank: predictions + loss (tol), "
+                              "table shards, Adam moments, MLP weights after 3 steps (tol_state)"}
         if args.exchange == "peer":
+            model, ok = None, True
             try:
                 model = PeerShardedDLRM(fc, BOT_MLP, TOP_MLP, seed=1234, pad_to=args.pad_to,
                                         row_wise_min_rows=args.row_wise_min_rows, gather=args.peer_gather,
                                         replicate_max_rows=args.replicate_max_rows)
             except Exception as e:   # no NVLink peer mapping on this box: NCCL all-to-all, table-wise
                 sys.stderr.write(f"bench.py: peer exchange unavailable ({e!r}); using --exchange nccl\n")
+                ok = False
+            if not all_ranks_ok(ok, torch.device("cuda", local_rank)):   # the fallback is collective
+                del model
                 args.exchange = "nccl"
                 model = ShardedDLRM(fc, BOT_MLP, TOP_MLP, seed=1234, pad_to=args.pad_to, exchange="nccl")
         else:
@@ -474,9 +510,14 @@ def run_b200(args):
                         "ms_per_step": ms_e2e / K},
                 "gpu_launches": per_step * K, "roofline": roof, "kernels": kernels,
                 "cpu_baseline": cpu, "final_loss": float(loss_host[-1])}
+        if parity is not None:
+            line["parity_check"] = parity
         print(json.dumps(line), flush=True)
     if world > 1:
         dist.destroy_process_group()
+    if parity is not None and not parity["ok"]:
+        sys.stderr.write(f"bench.py: multi-GPU parity check FAILED: {parity}\n")
+        sys.exit(3)
 
 
 def main():

@@ -336,6 +336,22 @@ int rtf_dense_gemm_tn(const float* d_a, int64_t lda, int64_t stride_a, const flo
                       int64_t stride_d, int M, int N, int K, int batch, void* d_ws, size_t ws_bytes,
                       void* stream);
 
+/* ---- dense optimizer steps (data-parallel replicas) ----------------------------------------
+ * replaces: the ResourceApplyAdam that model.compile(optimizer=Adam(learning_rate=1e-3)) runs on
+ *           every dense variable (src/ctr/fm/train.py:49-50; Keras form).
+ * rtf_dense_adam: ONE launch over a flat fp32 buffer of n parameters (n % 4 == 0, 16-byte
+ *   aligned) with its gradient and both moments; opt->lr carries the folded bias corrections
+ *   lr*sqrt(1-b2^t)/(1-b1^t); same separately rounded operations as K2's row update.
+ * rtf_rows_apply_dense: multi-GPU replicated small tables — K2's row update (l2 term, SGD /
+ *   Adagrad / Adam) on the rows r of a contiguous (rows, dim) block whose d_touched[r] > 0, from
+ *   the all-reduced summed gradients d_g (rows, dim).  Untouched rows and their state keep
+ *   their values (sparse-optimizer semantics, identical on every replica).                      */
+int rtf_dense_adam(float* d_w, const float* d_g, float* d_m, float* d_v, int64_t n,
+                   const rtf_opt* opt, void* stream);
+int rtf_rows_apply_dense(float* d_w, float* d_s1, float* d_s2, const float* d_g,
+                         const float* d_touched, int64_t rows, int dim, const rtf_opt* opt,
+                         void* stream);
+
 #ifdef __cplusplus
 }
 #endif

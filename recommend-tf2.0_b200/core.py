@@ -314,8 +314,18 @@ class BatchNormalization(Layer):
     def call(self, x, **kwargs):
         shp = x.shape
         x2 = x.reshape(-1, shp[-1])
-        y = F.batch_norm(x2, self.moving_mean, self.moving_variance, self.gamma, self.beta,
-                         self.training, 1.0 - self.momentum, self.epsilon)
+        if self.training:
+            # Keras updates moving_variance with the BIASED batch variance (torch's running_var
+            # takes the unbiased one), so the moving statistics are kept here and the
+            # normalisation itself (batch statistics, biased variance) goes through F.batch_norm
+            with torch.no_grad():
+                var, mean = torch.var_mean(x2, dim=0, unbiased=False)
+                self.moving_mean.mul_(self.momentum).add_(mean, alpha=1.0 - self.momentum)
+                self.moving_variance.mul_(self.momentum).add_(var, alpha=1.0 - self.momentum)
+            y = F.batch_norm(x2, None, None, self.gamma, self.beta, True, 0.0, self.epsilon)
+        else:
+            y = F.batch_norm(x2, self.moving_mean, self.moving_variance, self.gamma, self.beta,
+                             False, 0.0, self.epsilon)
         return y.reshape(shp)
 
 
@@ -347,6 +357,63 @@ class DNN(Layer):
         for dnn in self.dnn_network:
             x = dnn(x)
         return self.dropout(x)
+
+
+class DenseAdam:
+    """Keras-form Adam (App. A12; what every reference script compiles with,
+    src/ctr/fm/train.py:49-50) for the dense variables, as ONE kernel (rtf_dense_adam) over flat
+    buffers: the parameters are re-pointed at views of `flat`, their `.grad`s at views of
+    `flat_grad` (autograd accumulates into them in place), so a data-parallel trainer all-reduces
+    `flat_grad` directly and nothing is concatenated or copied back.  Same formulas and rounding
+    as K2's sparse row update, so embeddings and MLPs follow one Adam form:
+        m = b1 m + (1-b1) g;  v = b2 v + (1-b2) g^2;  w -= lr sqrt(1-b2^t)/(1-b1^t) m/(sqrt(v)+eps)"""
+
+    ALIGN = 64      # floats: every parameter starts on a 256-byte boundary (TMA / float4 loads)
+
+    def __init__(self, params, lr: float = 1e-3, beta1: float = 0.9, beta2: float = 0.999,
+                 eps: float = 1e-7):
+        from . import _lib as L
+        params = [p for p in params if p.requires_grad]
+        if not params:
+            raise ValueError("DenseAdam: no trainable parameters")
+        for p in params:
+            L.require_cuda(p, "DenseAdam(param)")
+            if p.dtype != torch.float32:
+                raise TypeError("DenseAdam: fp32 parameters only")
+        self.params, self.lr, self.beta1, self.beta2, self.eps = params, lr, beta1, beta2, eps
+        self.t = 0
+        offs, n = [], 0
+        for p in params:
+            offs.append(n)
+            n += (p.numel() + self.ALIGN - 1) // self.ALIGN * self.ALIGN
+        dev = params[0].device
+        self.flat = torch.zeros(n, dtype=torch.float32, device=dev)
+        self.flat_grad = torch.zeros_like(self.flat)
+        self.m = torch.zeros_like(self.flat)
+        self.v = torch.zeros_like(self.flat)
+        with torch.no_grad():
+            for p, o in zip(params, offs):
+                view = self.flat[o:o + p.numel()].view(p.shape)
+                view.copy_(p.data)
+                p.data = view
+                p.grad = self.flat_grad[o:o + p.numel()].view(p.shape)
+        self.offsets = offs
+
+    def zero_grad(self):
+        self.flat_grad.zero_()
+        for p, o in zip(self.params, self.offsets):     # someone may have set .grad to None
+            if p.grad is None or p.grad.data_ptr() != self.flat_grad.data_ptr() + 4 * o:
+                p.grad = self.flat_grad[o:o + p.numel()].view(p.shape)
+
+    def step(self):
+        import ctypes as C
+        from . import _lib as L
+        self.t += 1
+        lr_t = self.lr * math.sqrt(1.0 - self.beta2 ** self.t) / (1.0 - self.beta1 ** self.t)
+        st = L.rtf_opt(L.OPT_ADAM, lr_t, self.beta1, self.beta2, self.eps, 0.0)
+        L.check(L.lib().rtf_dense_adam(self.flat.data_ptr(), self.flat_grad.data_ptr(),
+                                       self.m.data_ptr(), self.v.data_ptr(), self.flat.numel(),
+                                       C.byref(st), L.current_stream_ptr()), "rtf_dense_adam")
 
 
 def binary_crossentropy(y_true: torch.Tensor, y_pred: torch.Tensor) -> torch.Tensor:

@@ -14,7 +14,7 @@ import torch
 
 from .embedding import EmbeddingTables, SparseOptimizer
 from .interaction import dot_out_cols, embed_dot
-from .core import DNN, Dense, Layer, binary_crossentropy
+from .core import DNN, Dense, DenseAdam, Layer, binary_crossentropy
 
 
 class DLRM(Layer):
@@ -53,9 +53,28 @@ class DLRM(Layer):
         return [p for p in self.parameters() if id(p) not in emb]
 
 
+def build_dense_layers(model, n_dense: int, device, n_tables: Optional[int] = None) -> None:
+    """Create the lazily built MLP weights (Keras layers build on first call) WITHOUT running the
+    model: a 4-row zero batch through the bottom / top stacks in eval mode (BatchNorm's moving
+    statistics do not move); none of the embedding-path kernels run."""
+    was_training = model.training
+    model.eval()
+    with torch.no_grad():
+        d = model.bot_dnn(torch.zeros(4, n_dense, device=device))
+        if getattr(model, "interaction", "dot") == "cat":
+            cols = sum(int(w.shape[1]) for w in model.embed_layers.weights) + d.shape[1]
+        else:
+            if n_tables is None:
+                n_tables = len(model.embed_layers.weights)
+            cols = dot_out_cols(n_tables + 1, d.shape[1], model.pad_to)
+        model.final_dense(model.top_dnn(torch.zeros(4, cols, device=device)))
+    model.train(was_training)
+
+
 class DLRMTrainer:
     """One training step = forward, Keras BCE, backward (K4 bwd -> K2 with the fused sparse
-    optimizer on the tables), dense Adam on the MLPs (Keras eps 1e-7)."""
+    optimizer on the tables), dense Adam on the MLPs (Keras form, core.DenseAdam: one
+    rtf_dense_adam launch over the flat parameter buffer)."""
 
     def __init__(self, model: DLRM, lr: float = 1e-3):
         self.model = model
@@ -66,13 +85,13 @@ class DLRMTrainer:
 
     def step(self, dense, sparse, labels) -> torch.Tensor:
         m = self.model
+        if self.dense_opt is None:      # layers build on first call: build them, then flatten
+            build_dense_layers(m, dense.shape[1], dense.device)
+            self.dense_opt = DenseAdam(m.dense_parameters(), lr=self.lr)
         m.embed_layers.begin_step()
         pred = m([dense, sparse])
-        if self.dense_opt is None:  # layers build on first call
-            self.dense_opt = torch.optim.Adam(m.dense_parameters(), lr=self.lr, eps=1e-7,
-                                              fused=dense.is_cuda)
         loss = binary_crossentropy(labels, pred)
-        self.dense_opt.zero_grad(set_to_none=True)
+        self.dense_opt.zero_grad()
         loss.backward()
         self.dense_opt.step()
         return loss.detach()

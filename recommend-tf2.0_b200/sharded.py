@@ -38,8 +38,9 @@ import torch
 import torch.distributed as dist
 
 from . import _lib as L
-from .core import DNN, Dense, Layer, binary_crossentropy
+from .core import DNN, Dense, DenseAdam, Layer, binary_crossentropy
 from .embedding import EmbeddingTables, SparseOptimizer, embed_bwd, embed_fwd
+from .dlrm import build_dense_layers
 from .interaction import dot_out_cols
 
 
@@ -91,6 +92,18 @@ class ShardLayout:
         g, j = self.slot_of[table]
         off, _ = self.block_offsets(B_local, D)
         return off[g] + j * D, self.T[g] * D
+
+
+def all_ranks_ok(ok: bool, device=None, group=None) -> bool:
+    """Collective agreement on a per-rank success flag (MIN over ranks): every rank must take the
+    same branch when the alternative is a different collective."""
+    if not (dist.is_available() and dist.is_initialized()) or dist.get_world_size(group) == 1:
+        return bool(ok)
+    if device is None or dist.get_backend(group) == "gloo":
+        device = torch.device("cpu")
+    flag = torch.tensor([1 if ok else 0], dtype=torch.int32, device=device)
+    dist.all_reduce(flag, op=dist.ReduceOp.MIN, group=group)
+    return bool(int(flag.item()))
 
 
 def exchange_ids(ids_local: torch.Tensor, world: int, group=None) -> torch.Tensor:
@@ -262,6 +275,7 @@ class ShardedDLRM(Layer):
         self.final_dense = Dense(1, activation=None)
         self._pending = None
         self._saved = None
+        self._out_inflight = False      # peers may still be pulling the previous forward's rows
         self.register_buffer("_mine_idx", torch.as_tensor(mine, dtype=torch.int64,
                                                           device=self.embed_layers.err.device))
 
@@ -273,11 +287,14 @@ class ShardedDLRM(Layer):
         local_ids = ids_global.index_select(1, self._mine_idx).contiguous()        # (B_global, T_me)
         self._saved = local_ids
         if self.exchange == "p2p":
+            ok = True
             try:
                 self._ensure_symmetric(B_local)
             except Exception as e:  # no peer access on this box: use the NCCL all-to-all instead
                 import warnings
                 warnings.warn(f"symmetric memory unavailable ({e}); row exchange falls back to NCCL")
+                ok = False
+            if not all_ranks_ok(ok, sparse_inputs.device):   # the choice of exchange is collective
                 self.exchange = "nccl"
         if self.exchange == "p2p":
             return self._call_p2p(dense_inputs, local_ids, B_local)
@@ -295,6 +312,10 @@ class ShardedDLRM(Layer):
         if self._sym_B == B_local:
             return
         import torch.distributed._symmetric_memory as symm
+        if self._sym_B is not None:     # peers may still address the old buffers: quiesce first
+            torch.cuda.synchronize()
+            dist.barrier()
+            self._out_inflight = False
         n = B_local * self.world * max(self.layout.T) * self.D       # same size on every rank
         dev = self.embed_layers.err.device
         self._out_buf = symm.empty(n, dtype=torch.float32, device=dev)
@@ -308,12 +329,15 @@ class ShardedDLRM(Layer):
         D, Tme = self.D, self.layout.T[self.rank]
         Bg = B_local * self.world
         out_view = self._out_buf[: Bg * Tme * D].view(Bg, Tme * D)
+        if self._out_inflight:      # no backward (grad barrier) since the last forward: peers may
+            self._out_hdl.barrier(channel=1)          # still be reading the previous batch's rows
         with torch.no_grad():
             embed_fwd(list(self.embed_layers.weights), local_ids, "BF", None,
                       err=self.embed_layers.err, out=out_view)
         dense_fea = self.bot_dnn(dense_inputs)
         self._out_hdl.barrier(channel=0)      # every owner's rows are in place (stream-ordered)
         x = _PeerInteractFn.apply(self, dense_fea, self.pad_to)
+        self._out_inflight = True
         return torch.sigmoid(self.final_dense(self.top_dnn(x)))
 
     def finish_backward(self):
@@ -322,6 +346,7 @@ class ShardedDLRM(Layer):
             return
         if self._pending == "p2p":
             self._grad_hdl.barrier(channel=0)  # all peers' dX rows have landed in my buffer
+            self._out_inflight = False         # ... so every peer is past its K4 forward as well
             D, Tme = self.D, self.layout.T[self.rank]
             Bg = self._sym_B * self.world
             grecv = self._grad_buf[: Bg * Tme * D].view(Bg, Tme * D)
@@ -343,7 +368,11 @@ class ShardedDLRM(Layer):
 class ShardedDLRMTrainer:
     """Per-rank step: local loss / world (so that summed gradients equal the global-batch mean,
     as MirroredStrategy scales them, App. A18), reverse exchange + K2 on owners, one flat
-    all-reduce of the MLP gradients, dense Adam."""
+    all-reduce of the MLP gradients, dense Adam (Keras form, core.DenseAdam).
+
+    The dense replicas are made identical BEFORE the first training forward: the MLP layers are
+    built on a dummy batch and rank 0's parameters and BatchNorm buffers are broadcast, so no
+    rank ever back-propagates activations computed with weights that were later overwritten."""
 
     def __init__(self, model: ShardedDLRM, lr: float = 1e-3):
         self.model, self.lr = model, lr
@@ -351,29 +380,32 @@ class ShardedDLRMTrainer:
             model.embed_layers.set_optimizer(SparseOptimizer("adam", lr=lr, l2=model.embed_reg))
         self.dense_opt = None
 
+    def _setup(self, dense):
+        m = self.model
+        build_dense_layers(m, dense.shape[1], dense.device, m.layout.n_tables)
+        params = m.dense_parameters()
+        emb = {id(b) for b in m.embed_layers.buffers()}
+        bufs = [b for n, b in m.named_buffers()
+                if id(b) not in emb and b.is_floating_point() and not n.startswith("_")]
+        for t in params + bufs:                            # same start on every rank
+            dist.broadcast(t.data, 0)
+        self.dense_opt = DenseAdam(params, lr=self.lr)
+
     def step(self, dense, sparse, labels) -> torch.Tensor:
         m = self.model
+        if self.dense_opt is None:
+            self._setup(dense)
         m.embed_layers.begin_step()
         pred = m([dense, sparse])
-        if self.dense_opt is None:
-            params = m.dense_parameters()
-            for p in params:                               # same start on every rank
-                dist.broadcast(p.data, 0)
-            self.dense_opt = torch.optim.Adam(params, lr=self.lr, eps=1e-7, fused=dense.is_cuda)
         loss = binary_crossentropy(labels, pred)
-        self.dense_opt.zero_grad(set_to_none=True)
+        self.dense_opt.zero_grad()
         (loss / m.world).backward()
-        # one flat all-reduce of the MLP gradients, asynchronous so that it overlaps the reverse
-        # exchange barrier + K2 on the embedding shards (finish_backward)
-        grads = [p.grad for p in m.dense_parameters() if p.grad is not None]
-        flat = torch.cat([g.reshape(-1) for g in grads])
-        work = dist.all_reduce(flat, async_op=True)
+        # one all-reduce of the persistent flat MLP-gradient buffer (no concat / copy-back),
+        # asynchronous so that it overlaps the reverse exchange barrier + K2 on the embedding
+        # shards (finish_backward)
+        work = dist.all_reduce(self.dense_opt.flat_grad, async_op=True)
         m.finish_backward()
         work.wait()
-        off = 0
-        for g in grads:
-            g.copy_(flat[off:off + g.numel()].view_as(g))
-            off += g.numel()
         self.dense_opt.step()
         return loss.detach()
 
@@ -640,6 +672,7 @@ class PeerShardedDLRM(Layer):
         self._grad_B = None
         self._pending = False
         self._prepared = None
+        self._out_inflight = False      # peers may still be pulling the previous forward's rows
         # replicated block: the shards of rep_fields are contiguous at the end of the table buffer
         self._Ts, self._Tr = len(lay.shard_fields[self.rank]), len(lay.rep_fields)
         self._rep_rows = [rows[t] for t in lay.rep_fields]
@@ -660,6 +693,10 @@ class PeerShardedDLRM(Layer):
         if self._grad_B == B_local:
             return
         import torch.distributed._symmetric_memory as symm
+        if self._grad_B is not None:    # peers may still address the old buffers: quiesce first
+            torch.cuda.synchronize()
+            dist.barrier()
+            self._out_inflight = False
         lay, D = self.layout, self.D
         dev = self._tab_buf.device
         n = B_local * self.world * lay.max_fields() * D
@@ -702,8 +739,9 @@ class PeerShardedDLRM(Layer):
         if owner:
             Tme = self._Ts + self._Tr
             Bg = B_local * self.world
-            if not train:       # no backward barrier between two forwards: peers may still be
-                self._out_hdl.barrier(channel=1)     # reading the previous batch's rows
+            if self._out_inflight:   # no grad barrier since the last forward (eval, or a forward
+                self._out_hdl.barrier(channel=1)     # never followed by finish_backward): peers may
+                #                                      still be reading the previous batch's rows
             out_view = self._out_buf[: Bg * Tme * self.D].view(Bg, Tme * self.D)
             W = list(self.embed_layers.weights)
             with torch.no_grad():
@@ -717,6 +755,7 @@ class PeerShardedDLRM(Layer):
         # step are complete before anyone pulls from the tables
         (self._out_hdl if owner else self._tab_hdl).barrier(channel=0)
         x = _PeerDotFn.apply(self, sparse_inputs, dense_fea, self.pad_to)
+        self._out_inflight = owner
         return torch.sigmoid(self.final_dense(self.top_dnn(x)))
 
     def finish_backward(self):
@@ -731,6 +770,7 @@ class PeerShardedDLRM(Layer):
         grad = self._grad_buf[: Bg * (Ts + Tr) * D].view(Bg, (Ts + Tr) * D)
         rep = self._reduce_replicated(grad[self.rank * Bl: (self.rank + 1) * Bl, Ts * D:]) if Tr else None
         self._grad_hdl.barrier(channel=0)
+        self._out_inflight = False      # every peer is past its K4 forward (it has pushed its dX)
         if Ts:
             self.embed_layers.apply_prepared(self._prepared, grad)
         if rep is not None:
@@ -777,3 +817,100 @@ class PeerShardedDLRM(Layer):
     def dense_parameters(self):
         emb = {id(p) for p in self.embed_layers.parameters()}
         return [p for p in self.parameters() if id(p) not in emb]
+
+
+# =============================================================================================
+# Self-check: sharded == single-GPU replica (used by bench.py at WORLD_SIZE > 1 and by tests)
+# =============================================================================================
+def parity_self_check(exchange: str = "peer", gather: str = "owner", replicate_max_rows: int = 70,
+                      steps: int = 3, F: int = 26, D: int = 32, B_local: int = 48,
+                      seed: int = 5) -> dict:
+    """Every rank trains the SAME small DLRM twice — sharded over the world (this rank's slice of
+    the global batch) and as a single-GPU replica on the whole global batch — and compares
+    predictions, loss, every table shard, its Adam moment and every MLP weight after `steps`
+    steps.  26 tables of 37 .. 312 rows so that, with row_wise_min_rows=200 and
+    replicate_max_rows=70, row-wise, table-wise AND replicated placements all occur (peer
+    exchange).  Eval forwards are interleaved with training ones (no gradient barrier between
+    two forwards: the peer-mapped row buffer must not be overwritten under a reader).  Returns
+    {"world", "modes", "max_rel_err", "max_rel_err_state", "ok", ...}; never raises on a
+    mismatch — the caller decides.  MirroredStrategy semantics (src/ctr/fm/train.py:43-50): the
+    sharded run must be indistinguishable from one replica seeing the global batch."""
+    from .dlrm import DLRM, DLRMTrainer
+    rank, world = dist.get_rank(), dist.get_world_size()
+    rows = [37 + 11 * t for t in range(F)]
+    fc = [[{"feat": f"I{i}"} for i in range(13)],
+          [{"feat": f"C{t}", "feat_num": rows[t], "embed_dim": D} for t in range(F)]]
+    kw = dict(bot_dnn_hidden_units=(64, D), top_dnn_hidden_units=(128, 64), input_bn=False)
+    single = DLRM(fc, seed=seed, **kw)
+    if exchange == "peer":
+        sharded = PeerShardedDLRM(fc, seed=seed, row_wise_min_rows=200, gather=gather,
+                                  replicate_max_rows=replicate_max_rows, **kw)
+        lay = sharded.layout
+        mine = lay.fields[rank]
+        kinds = sorted({"row-wise" if lay.row_wise[t] else "replicated" if lay.replicated[t]
+                        else "table-wise" for t in range(F)})
+
+        def shard_of(w, t):
+            return w[rank::world] if lay.row_wise[t] else w
+    else:
+        sharded = ShardedDLRM(fc, seed=seed, exchange=exchange, **kw)
+        mine = sharded.layout.slots[rank]
+        kinds = ["table-wise"]
+
+        def shard_of(w, t):
+            return w
+    g = torch.Generator(device="cuda").manual_seed(99)
+    B = B_local * world
+    dense = torch.rand(B, 13, device="cuda", generator=g)
+    sparse = torch.stack([torch.randint(0, r, (B,), device="cuda", generator=g) for r in rows],
+                         1).to(torch.int32)
+    y = (torch.rand(B, 1, device="cuda", generator=g) < 0.3).float()
+    sl = slice(rank * B_local, (rank + 1) * B_local)
+
+    err = {"fwd": 0.0, "state": 0.0}
+
+    def rel(a, b, key):
+        a, b = a.double(), b.double()
+        scale = float(b.abs().max()) or 1.0
+        err[key] = max(err[key], float((a - b).abs().max()) / scale)
+
+    t1 = DLRMTrainer(single, lr=1e-2)
+    t2 = ShardedDLRMTrainer(sharded, lr=1e-2)
+    build_dense_layers(single, 13, dense.device)
+    t2._setup(dense[sl])
+    with torch.no_grad():       # same start: single-GPU weights -> shards / replicas
+        for j, t in enumerate(mine):
+            sharded.embed_layers.weights[j].copy_(shard_of(single.embed_layers.weights[t], t))
+        for ps, pd in zip(single.dense_parameters(), sharded.dense_parameters()):
+            pd.copy_(ps)
+        rel(sharded([dense[sl], sparse[sl]]), single([dense, sparse])[sl], "fwd")
+        rel(sharded([dense[sl], sparse[sl]]), single([dense, sparse])[sl], "fwd")   # 2 forwards, no bwd
+    for _ in range(steps):
+        l1 = t1.step(dense, sparse, y)
+        l2 = t2.step(dense[sl], sparse[sl], y[sl])
+        lsum = l2.clone()
+        dist.all_reduce(lsum)
+        rel(lsum / world, l1, "fwd")
+        with torch.no_grad():   # eval forward between two training steps
+            rel(sharded([dense[sl], sparse[sl]]), single([dense, sparse])[sl], "fwd")
+    for j, t in enumerate(mine):
+        rel(sharded.embed_layers.weights[j], shard_of(single.embed_layers.weights[t], t), "state")
+        rel(sharded.embed_layers.state1[j], shard_of(single.embed_layers.state1[t], t), "state")
+        rel(sharded.embed_layers.state2[j], shard_of(single.embed_layers.state2[t], t), "state")
+    for ps, pd in zip(single.dense_parameters(), sharded.dense_parameters()):
+        rel(pd, ps, "state")
+    bad_ids = False
+    try:
+        sharded.embed_layers.check_ids()
+    except IndexError:
+        bad_ids = True
+    e = torch.tensor([err["fwd"], err["state"], float(bad_ids)], dtype=torch.float64, device="cuda")
+    dist.all_reduce(e, op=dist.ReduceOp.MAX)
+    torch.cuda.synchronize()
+    dist.barrier()      # nobody frees its peer-mapped buffers while a peer may still address them
+    fwd, state, bad = float(e[0]), float(e[1]), bool(e[2])
+    ok = (fwd <= 1e-5) and (state <= 1e-4) and not bad and fwd == fwd and state == state
+    mode = exchange + (f"/{gather}" if exchange == "peer" else "")
+    return {"world": world, "modes": [f"{mode}: {'+'.join(kinds)}"], "steps": steps,
+            "max_rel_err": fwd, "max_rel_err_state": state, "tol": 1e-5, "tol_state": 1e-4,
+            "ok": bool(ok)}

@@ -64,6 +64,48 @@ def test_attention_core_fwd_bwd_vs_torch(rtf, B, H, Lq, Lk, hs, masks):
         torch.testing.assert_close(a.grad, b_.grad, rtol=1e-4, atol=2e-5)
 
 
+@pytest.mark.parametrize("B,H,L,hs,form", [(4, 1, 200, 64, "match"), (8, 2, 39, 16, "ctr"),
+                                           (3, 1, 200, 64, "match-nomask")])
+def test_attention_core_vs_fp64_oracle(rtf, B, H, L, hs, form):
+    """The core kernel at the BASELINE shapes against the fp64 ORACLE (not torch fp32): forward
+    vs oracle.match_sdpa (src/match/layers/modules.py:76-96, query-row mask) / the ctr form's
+    QK^T * sqrt(hs) (src/ctr/layers/modules.py:235-239); gradients vs fp64 autograd over the same
+    formula.  Tolerance 1e-5 relative (north star), scale-aware atol."""
+    rng = np.random.default_rng(3)
+    q, k, v = (rng.normal(0, 1, (B, L, H * hs)) for _ in range(3))
+    mask = None
+    if form == "match":
+        lens = rng.integers(1, L + 1, B)
+        mask = (np.arange(L)[None, :] >= (L - lens)[:, None]).astype(np.float64)   # pre-padding
+        mask[0] = 0
+    sp = lambda t: np.transpose(t.reshape(B, L, H, hs), (0, 2, 1, 3))              # noqa: E731
+    if form.startswith("match"):
+        scale = 1.0 / math.sqrt(hs)
+        m4 = np.ones((B, H, L, 1)) if mask is None else np.tile(mask[:, None, :, None], (1, H, 1, 1))
+        want = OA.match_sdpa(sp(q), sp(k), sp(v), m4)
+    else:
+        scale = math.sqrt(hs)                       # the reference DIVIDES by hs ** -0.5
+        want = OA.softmax((sp(q) @ np.swapaxes(sp(k), -1, -2)) / (hs ** -0.5)) @ sp(v)
+    want = np.transpose(want, (0, 2, 1, 3)).reshape(B, L, H * hs)
+    tq, tk, tv = (_t(a, True) for a in (q, k, v))
+    rm = None if mask is None else _t(mask)
+    out = rtf.attention(tq, tk, tv, H, scale, rm, None, False)
+    g = rng.normal(0, 1, want.shape)
+    out.backward(_t(g))
+    _close(out.detach().cpu().numpy(), want, rtol=1e-5, atol=1e-5 * np.abs(want).max())
+    # fp64 gradients of the same formula
+    dq, dk, dv = (torch.from_numpy(a).double().requires_grad_(True) for a in (q, k, v))
+    tsp = lambda t: t.reshape(B, L, H, hs).transpose(1, 2)                         # noqa: E731
+    s = (tsp(dq) @ tsp(dk).transpose(-1, -2)) * scale
+    if mask is not None:
+        s = torch.where(torch.from_numpy(mask).reshape(B, 1, L, 1) == 0, torch.full_like(s, OA.PAD), s)
+    ref = (torch.softmax(s, -1) @ tsp(dv)).transpose(1, 2).reshape(B, L, H * hs)
+    ref.backward(torch.from_numpy(g))
+    for got, w in ((tq.grad, dq.grad), (tk.grad, dk.grad), (tv.grad, dv.grad)):
+        w = w.numpy()
+        _close(got.cpu().numpy(), w, rtol=1e-5, atol=1e-5 * np.abs(w).max())
+
+
 def test_fully_masked_row_is_exactly_uniform(rtf):
     """A6: every logit = pad -> softmax is exactly 1/L (SURVEY §8c known answer)."""
     B, L, hs = 2, 50, 16
