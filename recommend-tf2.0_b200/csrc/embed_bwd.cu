@@ -7,11 +7,18 @@
 // Pipeline, all on the caller's stream, no host sync:
 //   1. keys[p] = table(field(p)) << row_bits | id      (p = lookup position, ascending b,l,f)
 //   2. stable LSD radix sort of (key, p), 8 bits per pass over the significant bits only
-//   3. head flags + scan -> segment starts (one segment per touched row)
-//   4. segment reduce: one lane-group per segment adds its gradient rows in ascending p.
-//      Segments longer than RTF_SEG_CHUNK are split into fixed chunks whose partial sums
-//      are combined in chunk order — the summation tree depends only on the segment, so
-//      results are reproducible bit for bit — then the optimizer updates the row in place.
+//   3. head flags + scan -> segment starts (one segment per touched row); a second scan over the
+//      segments emits self-contained 16-byte WORK ITEMS: one per short segment
+//      {key, start, len, first lookup position} and one per RTF_SEG_CHUNK-row chunk of a long
+//      segment {key, start, len, long-segment slot}.  Steps 1-3 need only the ids and run on a
+//      side stream behind the dense MLP (rtf_embed_bwd_prepare).
+//   4. ONE persistent launch (seg_apply): a lane-group per item, the next item's record
+//      prefetched while the current one is processed, so an item costs one round of
+//      independent loads (gradient rows + W/m/v) instead of a 4-5 deep dependent chain.
+//      Short items add their gradient rows in ascending p and update the row in place.  Chunk
+//      items write their partial sum; the last chunk of a segment to arrive (atomic ticket)
+//      combines the partials IN CHUNK ORDER — the summation tree depends only on the segment,
+//      never on the arrival order, so results are reproducible bit for bit — and updates the row.
 // HBM-bound: per lookup one gradient row read, per touched row W/m/v read+write.
 #include <cstdlib>
 
@@ -62,22 +69,23 @@ constexpr int SCAN_THREADS = 256;
 constexpr int SCAN_ITEMS = 8;
 constexpr int SCAN_TILE = SCAN_THREADS * SCAN_ITEMS;
 
-__device__ __forceinline__ uint32_t block_exclusive_scan(uint32_t v, uint32_t* total) {
+template <typename T>
+__device__ __forceinline__ T block_exclusive_scan(T v, T* total) {
   // 256 threads; returns exclusive prefix of v across the block
-  __shared__ uint32_t warp_tot[SCAN_THREADS / 32];
+  __shared__ T warp_tot[SCAN_THREADS / 32];
   const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
-  uint32_t inc = v;
+  T inc = v;
 #pragma unroll
   for (int o = 1; o < 32; o <<= 1) {
-    uint32_t y = __shfl_up_sync(0xffffffffu, inc, o);
+    T y = __shfl_up_sync(0xffffffffu, inc, o);
     if (lane >= o) inc += y;
   }
   if (lane == 31) warp_tot[wid] = inc;
   __syncthreads();
-  uint32_t base = 0, tot = 0;
+  T base = 0, tot = 0;
 #pragma unroll
   for (int w = 0; w < SCAN_THREADS / 32; ++w) {
-    const uint32_t t = warp_tot[w];
+    const T t = warp_tot[w];
     if (w < wid) base += t;
     tot += t;
   }
@@ -86,48 +94,49 @@ __device__ __forceinline__ uint32_t block_exclusive_scan(uint32_t v, uint32_t* t
   return base + inc - v;
 }
 
-template <typename In>
+template <typename T, typename In>
 __global__ void __launch_bounds__(SCAN_THREADS)
-scan_tile_reduce(In in, long long n, uint32_t* __restrict__ tile_sums) {
+scan_tile_reduce(In in, long long n, T* __restrict__ tile_sums) {
   const long long base = (long long)blockIdx.x * SCAN_TILE + (long long)threadIdx.x * SCAN_ITEMS;
-  uint32_t s = 0;
+  T s = 0;
 #pragma unroll
   for (int k = 0; k < SCAN_ITEMS; ++k)
     if (base + k < n) s += in(base + k);
-  uint32_t tot;
-  block_exclusive_scan(s, &tot);
+  T tot;
+  block_exclusive_scan<T>(s, &tot);
   if (threadIdx.x == 0) tile_sums[blockIdx.x] = tot;
 }
 
-__global__ void __launch_bounds__(1024) scan_tile_sums(uint32_t* __restrict__ tile_sums, int nt) {
-  __shared__ uint32_t wsum[32];
-  __shared__ uint32_t carry_s;
+template <typename T>
+__global__ void __launch_bounds__(1024) scan_tile_sums(T* __restrict__ tile_sums, int nt) {
+  __shared__ T wsum[32];
+  __shared__ T carry_s;
   if (threadIdx.x == 0) carry_s = 0;
   __syncthreads();
   const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
   for (int base = 0; base < nt; base += 1024) {
     const int i = base + threadIdx.x;
-    const uint32_t v = i < nt ? tile_sums[i] : 0;
-    uint32_t inc = v;
+    const T v = i < nt ? tile_sums[i] : 0;
+    T inc = v;
 #pragma unroll
     for (int o = 1; o < 32; o <<= 1) {
-      uint32_t y = __shfl_up_sync(0xffffffffu, inc, o);
+      T y = __shfl_up_sync(0xffffffffu, inc, o);
       if (lane >= o) inc += y;
     }
     if (lane == 31) wsum[wid] = inc;
     __syncthreads();
     if (wid == 0) {
-      uint32_t w = wsum[lane], winc = w;
+      T w = wsum[lane], winc = w;
 #pragma unroll
       for (int o = 1; o < 32; o <<= 1) {
-        uint32_t y = __shfl_up_sync(0xffffffffu, winc, o);
+        T y = __shfl_up_sync(0xffffffffu, winc, o);
         if (lane >= o) winc += y;
       }
       wsum[lane] = winc - w;  // exclusive warp offsets
     }
     __syncthreads();
-    const uint32_t carry = carry_s;
-    const uint32_t excl = carry + wsum[wid] + inc - v;
+    const T carry = carry_s;
+    const T excl = carry + wsum[wid] + inc - v;
     if (i < nt) tile_sums[i] = excl;
     __syncthreads();
     if (threadIdx.x == 1023) carry_s = excl + v;
@@ -135,19 +144,19 @@ __global__ void __launch_bounds__(1024) scan_tile_sums(uint32_t* __restrict__ ti
   }
 }
 
-template <typename In, typename Out>
+template <typename T, typename In, typename Out>
 __global__ void __launch_bounds__(SCAN_THREADS)
-scan_tile_apply(In in, Out out, long long n, const uint32_t* __restrict__ tile_sums) {
+scan_tile_apply(In in, Out out, long long n, const T* __restrict__ tile_sums) {
   const long long base = (long long)blockIdx.x * SCAN_TILE + (long long)threadIdx.x * SCAN_ITEMS;
-  uint32_t v[SCAN_ITEMS];
-  uint32_t s = 0;
+  T v[SCAN_ITEMS];
+  T s = 0;
 #pragma unroll
   for (int k = 0; k < SCAN_ITEMS; ++k) {
     v[k] = base + k < n ? in(base + k) : 0;
     s += v[k];
   }
-  uint32_t tot;
-  uint32_t ex = block_exclusive_scan(s, &tot) + tile_sums[blockIdx.x];
+  T tot;
+  T ex = block_exclusive_scan<T>(s, &tot) + tile_sums[blockIdx.x];
 #pragma unroll
   for (int k = 0; k < SCAN_ITEMS; ++k) {
     if (base + k < n) out(base + k, ex, v[k]);
@@ -190,12 +199,63 @@ struct OutSegments {
   }
 };
 
-template <typename In, typename Out>
-static int exclusive_scan(In in, Out out, long long n, uint32_t* tile_sums, cudaStream_t st) {
+// Work items of step 4.  One uint4 each:
+//   short segment (len <= RTF_SEG_CHUNK): {key, start, len, vals[start]}      at items[cap_chunk + j]
+//   chunk c of a long segment:            {key, start + c*CH, len_c, slot0}   at items[slot0 + c]
+// slot0 = first chunk slot of the segment; long_seg[slot0] = {segment index, #chunks} and
+// arrive[slot0] is the segment's arrival counter.
+struct InSegKinds {  // low 32 bits: 1 for a short segment; high 32 bits: #chunks of a long one
+  const uint32_t* seg_start;
+  const int32_t* counters;
+  __device__ unsigned long long operator()(long long i) const {
+    if (i >= counters[1]) return 0ull;
+    const uint32_t len = seg_start[i + 1] - seg_start[i];
+    if (len <= RTF_SEG_CHUNK) return 1ull;
+    return (unsigned long long)((len + RTF_SEG_CHUNK - 1) / RTF_SEG_CHUNK) << 32;
+  }
+};
+struct OutItems {
+  const uint32_t* keys;
+  const uint32_t* vals;
+  const uint32_t* seg_start;
+  int32_t* counters;  // [2] = #short items, [3] = #chunk items
+  uint4* items;
+  uint32_t* short_seg;
+  uint2* long_seg;
+  uint32_t* arrive;
+  uint32_t cap_chunk;
+  __device__ void operator()(long long i, unsigned long long ex, unsigned long long v) const {
+    const int n_valid = counters[1];
+    if (i >= n_valid) return;
+    const uint32_t start = seg_start[i], len = seg_start[i + 1] - start;
+    const uint32_t key = keys[start];
+    if (v & 0xffffffffull) {
+      const uint32_t j = (uint32_t)ex;
+      items[cap_chunk + j] = make_uint4(key, start, len, vals[start]);
+      short_seg[j] = (uint32_t)i;
+    } else {
+      const uint32_t nch = (uint32_t)(v >> 32), slot0 = (uint32_t)(ex >> 32);
+      long_seg[slot0] = make_uint2((uint32_t)i, nch);
+      arrive[slot0] = 0u;
+      for (uint32_t c = 0; c < nch; ++c) {
+        const uint32_t s = start + c * RTF_SEG_CHUNK;
+        items[slot0 + c] = make_uint4(key, s, min((uint32_t)RTF_SEG_CHUNK, start + len - s), slot0);
+      }
+    }
+    if (i == n_valid - 1) {
+      const unsigned long long tot = ex + v;
+      counters[2] = (int)(uint32_t)tot;
+      counters[3] = (int)(uint32_t)(tot >> 32);
+    }
+  }
+};
+
+template <typename T, typename In, typename Out>
+static int exclusive_scan(In in, Out out, long long n, T* tile_sums, cudaStream_t st) {
   const long long nt = (n + SCAN_TILE - 1) / SCAN_TILE;
-  scan_tile_reduce<In><<<(unsigned)nt, SCAN_THREADS, 0, st>>>(in, n, tile_sums);
-  scan_tile_sums<<<1, 1024, 0, st>>>(tile_sums, (int)nt);
-  scan_tile_apply<In, Out><<<(unsigned)nt, SCAN_THREADS, 0, st>>>(in, out, n, tile_sums);
+  scan_tile_reduce<T, In><<<(unsigned)nt, SCAN_THREADS, 0, st>>>(in, n, tile_sums);
+  scan_tile_sums<T><<<1, 1024, 0, st>>>(tile_sums, (int)nt);
+  scan_tile_apply<T, In, Out><<<(unsigned)nt, SCAN_THREADS, 0, st>>>(in, out, n, tile_sums);
   RTF_CHECK_LAUNCH();
   return 0;
 }
@@ -334,17 +394,25 @@ __device__ __forceinline__ const float* grad_row(const BwdParams& P, const float
   return grad + (long long)b * P.grad_sb + lo + P.field_off[f];
 }
 
-// acc[k] (+)= rows vals[start..end) in ascending order, U loads in flight
+// acc[k] (+)= gradient rows of lookup positions vals[start..end) in ascending order, U loads
+// in flight.  `first_pos` (when have_first) is vals[start], already known from the work item.
 template <int VEC, int G, int VPL>
 __device__ __forceinline__ void sum_rows(const BwdParams& P, const float* __restrict__ grad,
                                          const uint32_t* __restrict__ vals, uint32_t start,
-                                         uint32_t end, int nv, int lg, float scale,
-                                         Vec<VEC> (&acc)[VPL]) {
+                                         uint32_t end, bool have_first, uint32_t first_pos, int nv,
+                                         int lg, float scale, Vec<VEC> (&acc)[VPL]) {
   constexpr int U = 4;
+#pragma unroll 1
   for (uint32_t j0 = start; j0 < end; j0 += U) {
     const float* src[U];
 #pragma unroll
-    for (int u = 0; u < U; ++u) src[u] = j0 + u < end ? grad_row(P, grad, vals[j0 + u]) : nullptr;
+    for (int u = 0; u < U; ++u) {
+      src[u] = nullptr;
+      if (j0 + u < end) {
+        const uint32_t p = (have_first && j0 + u == start) ? first_pos : __ldg(vals + j0 + u);
+        src[u] = grad_row(P, grad, p);
+      }
+    }
     Vec<VEC> x[U][VPL];
 #pragma unroll
     for (int u = 0; u < U; ++u)
@@ -450,124 +518,54 @@ __device__ __forceinline__ void finish_row(const BwdParams& P, uint32_t key, uin
 }
 
 struct SegWork {
-  const uint32_t* keys;       // sorted
   const uint32_t* vals;       // sorted lookup positions
-  const uint32_t* seg_start;  // [n_seg + 1]
-  int32_t* counters;          // [0] n_seg [1] n_valid [2] slots used [3] long segments
-  uint2* long_list;           // (seg, slot_base)
-  uint2* slot_owner;          // (seg, chunk)
-  float* partials;            // [slot][dim_max]
+  const int32_t* counters;    // [0] n_seg [1] n_valid [2] short items [3] chunk items
+  const uint4* items;         // [0, cap_chunk): chunk items; [cap_chunk, ...): short items
+  const uint32_t* short_seg;  // segment index of short item j (unique-row outputs only)
+  const uint2* long_seg;      // [slot0] = (segment index, #chunks)
+  uint32_t* arrive;           // [slot0] arrival counter of a long segment's chunks
+  float* partials;            // [chunk slot][dim_max]
   uint32_t* uniq_key;
   float* uniq_grad;
+  uint32_t cap_chunk;
   int dim_max;
 };
 
-// A: one lane-group per segment; short segments are finished here.
-// Tuning record (B200, DLRM cfg, ncu gpu__time_duration): the kernel is bound by a chain of
-// dependent memory round trips (seg_start -> key/vals -> gradient rows -> W/m/v), so resident
-// warps matter most: capping registers at 32 (64 warps/SM, ~90 B of spill) gives 511 us vs
-// 556 us at 48 registers; loading W/m/v before the gradient sum was slower at every register
-// cap tried (566-620 us), a persistent grid-stride variant 587 us.
+// Last chunk of a long segment to arrive: add the chunk partials IN CHUNK ORDER (whoever runs
+// this, the summation tree is the same), then update the row.  Kept out of line: it is rare and
+// must not cost the streaming path registers.
 template <int VEC, int G, int VPL>
-__global__ void __launch_bounds__(256, VPL == 1 ? 8 : 4)
-seg_short(const __grid_constant__ BwdParams P, const __grid_constant__ SegWork S,
-          const float* __restrict__ grad) {
-  const long long gid = ((long long)blockIdx.x * blockDim.x + threadIdx.x) / G;
-  const int lg = (int)(threadIdx.x % G);
-  if (gid >= S.counters[1]) return;  // invalid-id segment (if any) is the last one
-  const uint32_t seg = (uint32_t)gid;
-  const uint32_t start = S.seg_start[seg], end = S.seg_start[seg + 1];
-  const uint32_t key = S.keys[start];
-  const uint32_t len = end - start;
-  if (len > RTF_SEG_CHUNK) {
-    const uint32_t nch = (len + RTF_SEG_CHUNK - 1) / RTF_SEG_CHUNK;
-    uint32_t slot0 = 0;
-    if (lg == 0) {
-      slot0 = (uint32_t)atomicAdd(&S.counters[2], (int)nch);
-      const int e = atomicAdd(&S.counters[3], 1);
-      S.long_list[e] = make_uint2(seg, slot0);
-    }
-    if (G > 1) {  // broadcast inside the lane-group only: other groups of the warp may not be here
-      const int g0 = (int)(threadIdx.x & 31) / G * G;
-      const uint32_t gmask = G == 32 ? 0xffffffffu : (((1u << (G & 31)) - 1u) << g0);
-      slot0 = __shfl_sync(gmask, slot0, g0);
-    }
-    for (uint32_t c = lg; c < nch; c += G) S.slot_owner[slot0 + c] = make_uint2(seg, c);
-    return;
-  }
-  const int nv = P.dim[key >> P.row_bits] / VEC;
+__device__ __noinline__ void combine_long(const BwdParams& P, const SegWork& S, uint32_t key,
+                                          uint32_t slot0, uint2 ls, int nv, int lg) {
+  __threadfence();
+  if (lg == 0) S.arrive[slot0] = 0u;  // the prepared work list can be applied again
   Vec<VEC> acc[VPL];
 #pragma unroll
   for (int k = 0; k < VPL; ++k)
 #pragma unroll
     for (int e = 0; e < VEC; ++e) acc[k].v[e] = 0.f;
-  const float scale = __fdiv_rn(1.0f, (float)P.L);
-  sum_rows<VEC, G, VPL>(P, grad, S.vals, start, end, nv, lg, scale, acc);
-  RowState<VEC, VPL> st;
-  load_row_state<VEC, G, VPL>(P, key, nv, lg, st);
-  finish_row<VEC, G, VPL>(P, key, seg, nv, lg, acc, st, S.uniq_key, S.uniq_grad, S.dim_max);
-}
-
-// B: one lane-group per chunk of a long segment -> partial sums
-template <int VEC, int G, int VPL>
-__global__ void __launch_bounds__(256, VPL == 1 ? 8 : 4)
-seg_partial(const __grid_constant__ BwdParams P, const __grid_constant__ SegWork S,
-            const float* __restrict__ grad) {
-  const long long gid = ((long long)blockIdx.x * blockDim.x + threadIdx.x) / G;
-  const int lg = (int)(threadIdx.x % G);
-  if (gid >= S.counters[2]) return;
-  const uint2 own = S.slot_owner[gid];
-  const uint32_t s0 = S.seg_start[own.x], s1 = S.seg_start[own.x + 1];
-  const uint32_t start = s0 + own.y * RTF_SEG_CHUNK;
-  const uint32_t end = min(start + RTF_SEG_CHUNK, s1);
-  const uint32_t key = S.keys[s0];
-  const int nv = P.dim[key >> P.row_bits] / VEC;
-  Vec<VEC> acc[VPL];
-#pragma unroll
-  for (int k = 0; k < VPL; ++k)
-#pragma unroll
-    for (int e = 0; e < VEC; ++e) acc[k].v[e] = 0.f;
-  const float scale = __fdiv_rn(1.0f, (float)P.L);
-  sum_rows<VEC, G, VPL>(P, grad, S.vals, start, end, nv, lg, scale, acc);
-#pragma unroll
-  for (int k = 0; k < VPL; ++k) {
-    const int vi = lg + k * G;
-    if (vi < nv) vstore<VEC>(S.partials + gid * S.dim_max + VEC * vi, acc[k]);
-  }
-}
-
-// C: one lane-group per long segment combines its chunk partials in chunk order
-template <int VEC, int G, int VPL>
-__global__ void __launch_bounds__(256, VPL == 1 ? 8 : 4)
-seg_combine(const __grid_constant__ BwdParams P, const __grid_constant__ SegWork S) {
-  const long long gid = ((long long)blockIdx.x * blockDim.x + threadIdx.x) / G;
-  const int lg = (int)(threadIdx.x % G);
-  if (gid >= S.counters[3]) return;
-  const uint2 ent = S.long_list[gid];
-  const uint32_t seg = ent.x;
-  const uint32_t start = S.seg_start[seg], end = S.seg_start[seg + 1];
-  const uint32_t nch = (end - start + RTF_SEG_CHUNK - 1) / RTF_SEG_CHUNK;
-  const uint32_t key = S.keys[start];
-  const int nv = P.dim[key >> P.row_bits] / VEC;
-  Vec<VEC> acc[VPL];
-#pragma unroll
-  for (int k = 0; k < VPL; ++k)
-#pragma unroll
-    for (int e = 0; e < VEC; ++e) acc[k].v[e] = 0.f;
-  constexpr int U = VPL == 1 ? 16 : 4;  // partials are contiguous and L2-resident: go deep
-  for (uint32_t c0 = 0; c0 < nch; c0 += U) {
+  constexpr int U = 4;  // partials are contiguous and L2-resident
+#pragma unroll 1
+  for (uint32_t c0 = 0; c0 < ls.y; c0 += U) {
     Vec<VEC> x[U][VPL];
 #pragma unroll
     for (int u = 0; u < U; ++u)
 #pragma unroll
       for (int k = 0; k < VPL; ++k) {
         const int vi = lg + k * G;
-        if (c0 + u < nch && vi < nv)
-          x[u][k] = vload<VEC>(S.partials + (long long)(ent.y + c0 + u) * S.dim_max + VEC * vi);
+        if (c0 + u < ls.y && vi < nv) {
+          const float* src = S.partials + (long long)(slot0 + c0 + u) * S.dim_max + VEC * vi;
+          if constexpr (VEC == 4) {
+            const float4 t = __ldcg(reinterpret_cast<const float4*>(src));
+            x[u][k].v[0] = t.x; x[u][k].v[1] = t.y; x[u][k].v[2] = t.z; x[u][k].v[3] = t.w;
+          } else {
+            x[u][k].v[0] = __ldcg(src);
+          }
+        }
       }
 #pragma unroll
     for (int u = 0; u < U; ++u)
-      if (c0 + u < nch) {
+      if (c0 + u < ls.y) {
 #pragma unroll
         for (int k = 0; k < VPL; ++k) {
           const int vi = lg + k * G;
@@ -580,27 +578,122 @@ seg_combine(const __grid_constant__ BwdParams P, const __grid_constant__ SegWork
   }
   RowState<VEC, VPL> st;
   load_row_state<VEC, G, VPL>(P, key, nv, lg, st);
-  finish_row<VEC, G, VPL>(P, key, seg, nv, lg, acc, st, S.uniq_key, S.uniq_grad, S.dim_max);
+  finish_row<VEC, G, VPL>(P, key, ls.x, nv, lg, acc, st, S.uniq_key, S.uniq_grad, S.dim_max);
 }
 
-template <int VEC, int G, int VPL>
-static int launch_segments(const BwdParams& P, const SegWork& S, const float* grad, long long n,
-                           cudaStream_t st) {
-  const long long groups_a = n;                            // upper bound on segments
-  const long long groups_b = 2 * n / RTF_SEG_CHUNK + 2;    // upper bound on chunk slots
-  const long long groups_c = n / RTF_SEG_CHUNK + 1;        // upper bound on long segments
-  seg_short<VEC, G, VPL><<<(unsigned)((groups_a * G + 255) / 256), 256, 0, st>>>(P, S, grad);
-  seg_partial<VEC, G, VPL><<<(unsigned)((groups_b * G + 255) / 256), 256, 0, st>>>(P, S, grad);
-  seg_combine<VEC, G, VPL><<<(unsigned)((groups_c * G + 255) / 256), 256, 0, st>>>(P, S);
+// One launch, one lane-group of G lanes per work item (chunk items first, then short segments).
+// The item record carries everything the group needs, so an item costs one round of independent
+// loads: for the common 1-2 row segment the gradient rows and the row's W/m/v are all in flight
+// together; longer segments stream their gradient rows 4 at a time and load W/m/v afterwards
+// (fewer live registers; measured: the kernel lives on resident warps, spills are fatal).
+template <int VEC, int G, int VPL, int MINB>
+__global__ void __launch_bounds__(256, MINB)
+seg_apply(const __grid_constant__ BwdParams P, const __grid_constant__ SegWork S,
+          const float* __restrict__ grad) {
+  const uint32_t i = (uint32_t)(((long long)blockIdx.x * 256 + threadIdx.x) / G);
+  const uint32_t n_chunk = (uint32_t)S.counters[3];
+  if (i >= n_chunk + (uint32_t)S.counters[2]) return;
+  const int lg = (int)(threadIdx.x % G);
+  const uint4 rec = __ldg(S.items + (i < n_chunk ? i : S.cap_chunk + (i - n_chunk)));
+  const uint32_t key = rec.x, start = rec.y, len = rec.z;
+  const int nv = P.dim[key >> P.row_bits] / VEC;
+  const float scale = __fdiv_rn(1.0f, (float)P.L);
+  Vec<VEC> acc[VPL];
+#pragma unroll
+  for (int k = 0; k < VPL; ++k)
+#pragma unroll
+    for (int e = 0; e < VEC; ++e) acc[k].v[e] = 0.f;
+  if (i >= n_chunk) {
+    // ---- short segment
+    RowState<VEC, VPL> st;
+    if (len <= 2) {
+      // everything in one round: W/m/v and up to two gradient rows
+      load_row_state<VEC, G, VPL>(P, key, nv, lg, st);
+      const float* r0 = grad_row(P, grad, rec.w);
+      const float* r1 = len == 2 ? grad_row(P, grad, __ldg(S.vals + start + 1)) : nullptr;
+      Vec<VEC> x0[VPL], x1[VPL];
+#pragma unroll
+      for (int k = 0; k < VPL; ++k) {
+        const int vi = lg + k * G;
+        if (vi < nv) {
+          x0[k] = vload_stream<VEC>(r0 + VEC * vi);
+          if (r1) x1[k] = vload_stream<VEC>(r1 + VEC * vi);
+        }
+      }
+#pragma unroll
+      for (int k = 0; k < VPL; ++k) {
+        const int vi = lg + k * G;
+        if (vi < nv) {
+#pragma unroll
+          for (int e = 0; e < VEC; ++e) {
+            float g = x0[k].v[e];
+            if (P.pool == RTF_POOL_MEAN) g = __fmul_rn(g, scale);
+            acc[k].v[e] = __fadd_rn(acc[k].v[e], g);
+            if (r1) {
+              float h = x1[k].v[e];
+              if (P.pool == RTF_POOL_MEAN) h = __fmul_rn(h, scale);
+              acc[k].v[e] = __fadd_rn(acc[k].v[e], h);
+            }
+          }
+        }
+      }
+    } else {
+      sum_rows<VEC, G, VPL>(P, grad, S.vals, start, start + len, true, rec.w, nv, lg, scale, acc);
+      load_row_state<VEC, G, VPL>(P, key, nv, lg, st);
+    }
+    uint32_t seg = 0;
+    if (S.uniq_key || S.uniq_grad) seg = __ldg(S.short_seg + (i - n_chunk));
+    finish_row<VEC, G, VPL>(P, key, seg, nv, lg, acc, st, S.uniq_key, S.uniq_grad, S.dim_max);
+    return;
+  }
+  // ---- chunk of a long segment: partial sum; the last chunk to arrive combines in chunk order
+  const int g0 = (int)(threadIdx.x & 31) / G * G;  // first lane of this group inside its warp
+  const uint32_t gmask = G == 32 ? 0xffffffffu : (((1u << (G & 31)) - 1u) << g0);
+  const uint32_t slot0 = rec.w;
+  sum_rows<VEC, G, VPL>(P, grad, S.vals, start, start + len, false, 0u, nv, lg, scale, acc);
+#pragma unroll
+  for (int k = 0; k < VPL; ++k) {
+    const int vi = lg + k * G;
+    if (vi < nv) vstore<VEC>(S.partials + (long long)i * S.dim_max + VEC * vi, acc[k]);
+  }
+  __threadfence();
+  __syncwarp(gmask);
+  const uint2 ls = __ldg(S.long_seg + slot0);  // (segment index, #chunks)
+  uint32_t ticket = 0;
+  if (lg == 0) ticket = atomicAdd(S.arrive + slot0, 1u);
+  ticket = __shfl_sync(gmask, ticket, g0);
+  if (ticket == ls.y - 1) combine_long<VEC, G, VPL>(P, S, key, slot0, ls, nv, lg);
+}
+
+template <int VEC, int G, int VPL, int MINB>
+static int launch_apply(const BwdParams& P, const SegWork& S, const float* grad,
+                        long long max_items, cudaStream_t st) {
+  const long long blocks = (max_items * G + 255) / 256;
+  seg_apply<VEC, G, VPL, MINB><<<(unsigned)blocks, 256, 0, st>>>(P, S, grad);
   RTF_CHECK_LAUNCH();
   return 0;
+}
+
+// Tuning record (B200, DLRM cfg: 26 tables, D = 128, B = 65 536, uniform ids; CUDA events):
+//   round 1 (seg_short + seg_partial + seg_combine, 4-5 dependent loads per segment)  0.67 ms
+//   persistent grid-stride groups with the next record prefetched, W/m/v early:
+//     48 regs 0.94 ms, 64 regs 0.84 ms — 150-400 B of spills per thread go to L2 and sit on
+//     every item's critical path; occupancy 32-40 warps/SM
+//   this kernel, one item per group, resident blocks/SM 4 / 5 / 6 / 8 (56 / 48 / 40 / 32 regs):
+//     0.539 / 0.498 / 0.498 / 0.472 ms  -> 8 blocks (64 warps/SM, ~110 B spill) = 5.3 TB/s,
+//     0.81 of the measured HBM copy peak.
+template <int VEC, int G, int VPL>
+static int launch_segments(const BwdParams& P, const SegWork& S, const float* grad,
+                           long long max_items, cudaStream_t st) {
+  return launch_apply<VEC, G, VPL, (VPL == 1 ? 8 : 4)>(P, S, grad, max_items, st);
 }
 
 static inline size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
 
 struct WsLayout {
-  size_t keys0, keys1, vals0, vals1, hist, tile_sums, seg_start, counters, long_list, slot_owner,
-      partials, total;
+  size_t keys0, keys1, vals0, vals1, hist, tile_sums, seg_start, counters, items, short_seg,
+      long_seg, arrive, partials, total;
+  size_t cap_chunk;
 };
 static WsLayout ws_layout(long long n, int dim_max) {
   WsLayout w;
@@ -614,12 +707,16 @@ static WsLayout ws_layout(long long n, int dim_max) {
   w.vals1 = take(nn * 4);
   w.hist = take((size_t)SORT_MAX_BINS * nblk * 4);
   const size_t scan_n = nn > (size_t)SORT_MAX_BINS * nblk ? nn : (size_t)SORT_MAX_BINS * nblk;
-  w.tile_sums = take(((scan_n + SCAN_TILE - 1) / SCAN_TILE + 1) * 4);
+  w.tile_sums = take(((scan_n + SCAN_TILE - 1) / SCAN_TILE + 1) * 8);
   w.seg_start = take((nn + 1) * 4);
   w.counters = take(16);
-  w.long_list = take((nn / RTF_SEG_CHUNK + 2) * 8);
-  w.slot_owner = take((2 * nn / RTF_SEG_CHUNK + 4) * 8);
-  w.partials = take((2 * nn / RTF_SEG_CHUNK + 4) * (size_t)dim_max * 4);
+  // a long segment of len > CH rows has ceil(len/CH) <= 2 len/CH chunks: at most 2n/CH slots
+  w.cap_chunk = 2 * nn / RTF_SEG_CHUNK + 4;
+  w.items = take((w.cap_chunk + nn) * 16);
+  w.short_seg = take(nn * 4);
+  w.long_seg = take(w.cap_chunk * 8);
+  w.arrive = take(w.cap_chunk * 4);
+  w.partials = take(w.cap_chunk * (size_t)dim_max * 4);
   w.total = o;
   return w;
 }
@@ -743,7 +840,8 @@ static int embed_bwd_impl(int phase, float* const* weights, float* const* state1
   // 2. LSD radix sort over the significant bits
   for (int shift = 0, pass = 0; pass < npass; shift += bits, ++pass) {
     sort_hist<<<nblk, SORT_THREADS, 0, st>>>(keys[cur], n, shift, bits, hist, nblk);
-    int rc = exclusive_scan(InArray{hist}, OutArray{hist}, (long long)(1 << bits) * nblk, tile_sums, st);
+    int rc = exclusive_scan<uint32_t>(InArray{hist}, OutArray{hist}, (long long)(1 << bits) * nblk,
+                                      tile_sums, st);
     if (rc) return rc;
     sort_scatter<<<nblk, SORT_THREADS, 0, st>>>(keys[cur], vals[cur], keys[cur ^ 1],
                                                 vals[cur ^ 1], n, shift, bits, hist, nblk,
@@ -758,7 +856,16 @@ static int embed_bwd_impl(int phase, float* const* weights, float* const* state1
   {
     OutSegments outseg{keys[cur], seg_start, counters, d_num_uniq, n, (uint32_t)n_tables,
                        row_bits};
-    int rc = exclusive_scan(InHeadFlag{keys[cur]}, outseg, n, tile_sums, st);
+    int rc = exclusive_scan<uint32_t>(InHeadFlag{keys[cur]}, outseg, n, tile_sums, st);
+    if (rc) return rc;
+  }
+  // 3b. work items: one per short segment, one per chunk of a long segment
+  {
+    OutItems outit{keys[cur], vals[cur], seg_start, counters, (uint4*)(ws + W.items),
+                   (uint32_t*)(ws + W.short_seg), (uint2*)(ws + W.long_seg),
+                   (uint32_t*)(ws + W.arrive), (uint32_t)W.cap_chunk};
+    int rc = exclusive_scan<unsigned long long>(InSegKinds{seg_start, counters}, outit, n,
+                                                (unsigned long long*)tile_sums, st);
     if (rc) return rc;
   }
   }  // phase & 1
@@ -766,17 +873,32 @@ static int embed_bwd_impl(int phase, float* const* weights, float* const* state1
 
   // 4. segment reduce + optimizer
   SegWork S;
-  S.keys = keys[cur];
   S.vals = vals[cur];
-  S.seg_start = seg_start;
   S.counters = counters;
-  S.long_list = (uint2*)(ws + W.long_list);
-  S.slot_owner = (uint2*)(ws + W.slot_owner);
+  S.items = (const uint4*)(ws + W.items);
+  S.short_seg = (const uint32_t*)(ws + W.short_seg);
+  S.long_seg = (const uint2*)(ws + W.long_seg);
+  S.arrive = (uint32_t*)(ws + W.arrive);
   S.partials = (float*)(ws + W.partials);
   S.uniq_key = d_uniq_key;
   S.uniq_grad = d_uniq_grad;
+  S.cap_chunk = (uint32_t)W.cap_chunk;
   S.dim_max = dim_max;
 
+  // upper bound on the work items: a table with n_t lookups and R_t rows has at most
+  // min(n_t, R_t) segments and n_t/CH + min(R_t, n_t/CH) chunks of long segments
+  long long max_items = 0;
+  {
+    long long per_table[RTF_MAX_FIELDS] = {};
+    for (int f = 0; f < n_fields; ++f) per_table[field_table[f]] += B * (long long)L;
+    for (int t = 0; t < n_tables; ++t) {
+      const long long nt = per_table[t];
+      const long long b = rows[t] + 2 * (nt / RTF_SEG_CHUNK) + 2;
+      max_items += nt < b ? nt : b;
+    }
+    if (max_items > n) max_items = n;
+    if (max_items < 1) max_items = 1;
+  }
   if (vec_ok) {
     const int nv = dim_max / 4;
     int G = 1;
@@ -784,16 +906,16 @@ static int embed_bwd_impl(int phase, float* const* weights, float* const* state1
     const int vpl = (nv + G - 1) / G;
     if (vpl == 1) {
       switch (G) {
-        case 1: return launch_segments<4, 1, 1>(P, S, d_grad, n, st);
-        case 2: return launch_segments<4, 2, 1>(P, S, d_grad, n, st);
-        case 4: return launch_segments<4, 4, 1>(P, S, d_grad, n, st);
-        case 8: return launch_segments<4, 8, 1>(P, S, d_grad, n, st);
-        case 16: return launch_segments<4, 16, 1>(P, S, d_grad, n, st);
-        default: return launch_segments<4, 32, 1>(P, S, d_grad, n, st);
+        case 1: return launch_segments<4, 1, 1>(P, S, d_grad, max_items, st);
+        case 2: return launch_segments<4, 2, 1>(P, S, d_grad, max_items, st);
+        case 4: return launch_segments<4, 4, 1>(P, S, d_grad, max_items, st);
+        case 8: return launch_segments<4, 8, 1>(P, S, d_grad, max_items, st);
+        case 16: return launch_segments<4, 16, 1>(P, S, d_grad, max_items, st);
+        default: return launch_segments<4, 32, 1>(P, S, d_grad, max_items, st);
       }
     }
-    if (vpl == 2) return launch_segments<4, 32, 2>(P, S, d_grad, n, st);
-    return launch_segments<4, 32, 4>(P, S, d_grad, n, st);
+    if (vpl == 2) return launch_segments<4, 32, 2>(P, S, d_grad, max_items, st);
+    return launch_segments<4, 32, 4>(P, S, d_grad, max_items, st);
   }
   {
     int G = 1;
@@ -801,16 +923,16 @@ static int embed_bwd_impl(int phase, float* const* weights, float* const* state1
     const int vpl = (dim_max + G - 1) / G;
     if (vpl == 1) {
       switch (G) {
-        case 1: return launch_segments<1, 1, 1>(P, S, d_grad, n, st);
-        case 2: return launch_segments<1, 2, 1>(P, S, d_grad, n, st);
-        case 4: return launch_segments<1, 4, 1>(P, S, d_grad, n, st);
-        case 8: return launch_segments<1, 8, 1>(P, S, d_grad, n, st);
-        case 16: return launch_segments<1, 16, 1>(P, S, d_grad, n, st);
-        default: return launch_segments<1, 32, 1>(P, S, d_grad, n, st);
+        case 1: return launch_segments<1, 1, 1>(P, S, d_grad, max_items, st);
+        case 2: return launch_segments<1, 2, 1>(P, S, d_grad, max_items, st);
+        case 4: return launch_segments<1, 4, 1>(P, S, d_grad, max_items, st);
+        case 8: return launch_segments<1, 8, 1>(P, S, d_grad, max_items, st);
+        case 16: return launch_segments<1, 16, 1>(P, S, d_grad, max_items, st);
+        default: return launch_segments<1, 32, 1>(P, S, d_grad, max_items, st);
       }
     }
-    if (vpl == 2) return launch_segments<1, 32, 2>(P, S, d_grad, n, st);
-    return launch_segments<1, 32, 4>(P, S, d_grad, n, st);
+    if (vpl == 2) return launch_segments<1, 32, 2>(P, S, d_grad, max_items, st);
+    return launch_segments<1, 32, 4>(P, S, d_grad, max_items, st);
   }
 }
 

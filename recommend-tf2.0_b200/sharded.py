@@ -870,7 +870,7 @@ def parity_self_check(exchange: str = "peer", gather: str = "owner", replicate_m
     err = {"fwd": 0.0, "state": 0.0}
 
     def rel(a, b, key):
-        a, b = a.double(), b.double()
+        a, b = a.detach().double(), b.detach().double()
         scale = float(b.abs().max()) or 1.0
         err[key] = max(err[key], float((a - b).abs().max()) / scale)
 
