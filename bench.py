@@ -38,6 +38,10 @@ def parse_args():
     ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--workload", default="dlrm",
+                    choices=["dlrm", "fm", "din", "autoint", "sasrec", "youtubednn"],
+                    help="dlrm = BASELINE.json's metric config (configs[1], default); the others are "
+                         "configs[0], [2], [3], [4] (bench_workloads.py): same contract line each")
     ap.add_argument("--batch", type=int, default=65536, help="samples per GPU per step")
     ap.add_argument("--ids", default="uniform", choices=["uniform", "zipf"])
     ap.add_argument("--cpu-batch", type=int, default=2048)
@@ -520,8 +524,138 @@ def run_b200(args):
         sys.exit(3)
 
 
+def run_workload_reference(args):
+    """--impl reference for a non-DLRM workload: its CPU port on the host cores."""
+    if int(os.environ.get("RANK", "0")) != 0:
+        return
+    import bench_workloads as BW
+    wl = BW.WORKLOADS[args.workload]()
+    r = BW.run_cpu(wl, steps=args.steps, warmup=max(args.warmup, 1))
+    cfg = dict(wl.config(), batch_per_gpu=wl.cpu_batch, global_batch=wl.cpu_batch,
+               parallelism="host cores, one process", same_config=wl.cpu_batch == wl.batch)
+    line = {"metric": wl.metric, "value": r["value"], "unit": "samples/s", "impl": "reference",
+            "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": r["ms_per_step"],
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
+            "data": "synthetic", "config": cfg,
+            "cpu_baseline": {k: r[k] for k in ("value", "unit", "cores", "kind", "sample")},
+            "e2e": {"value": r["value"], "unit": "samples/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+    print(json.dumps(line), flush=True)
+
+
+def run_workload(args):
+    """A non-DLRM BASELINE config through the same protocol: W warm-up steps, K timed steps on
+    device-resident batches (value), K steps from pinned host batches through DeviceFeeder with the
+    loss read back every step (e2e), the model's dominant hot-path kernel against its roofline,
+    the CPU port beside it.  N > 1 = N independent replicas (these paths do not shard)."""
+    import numpy as np
+    import torch
+    import torch.distributed as dist
+    import bench_workloads as BW
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device — the B200 path has no CPU fallback "
+                         "(use --impl reference for the host baseline)")
+    torch.cuda.set_device(local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    torch.backends.cuda.matmul.allow_tf32 = False
+    torch.backends.cudnn.allow_tf32 = False
+    import recommend_tf2_b200 as pkg
+    pkg.lib()
+    peaks, peak_src = load_peaks()
+    wl = BW.WORKLOADS[args.workload]()
+    B = wl.batch
+    K, W = args.steps, max(args.warmup, 3)
+    st = wl.build(pkg)
+    rng = np.random.default_rng(1000 + rank)
+    host = [tuple(torch.from_numpy(np.ascontiguousarray(a)).pin_memory() for a in wl.host_batch(rng, B))
+            for _ in range(W + K)]
+    dev = [tuple(t.cuda(non_blocking=True) for t in b) for b in host]
+    torch.cuda.synchronize()
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    sampler = ClockSampler(local_rank) if rank == 0 else None
+    for i in range(W):
+        st.step(*dev[i])
+    barrier()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    t_start = time.time()
+    e0.record()
+    for i in range(W, W + K):
+        st.step(*dev[i])
+    e1.record()
+    barrier()
+    t_end = time.time()
+    ms_total = e0.elapsed_time(e1)
+    clocks = sampler.stop(t_start, t_end) if sampler else None
+
+    loss_host = torch.zeros(K, dtype=torch.float32).pin_memory()
+    for _ in pkg.DeviceFeeder(host[:2]):
+        pass
+    barrier()
+    f0, f1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    f0.record()
+    for i, b in enumerate(pkg.DeviceFeeder(host[W:W + K])):
+        loss_host[i].copy_(st.step(*b), non_blocking=True)
+    f1.record()
+    barrier()
+    ms_e2e = f0.elapsed_time(f1)
+    for ts in st.trainer.tables:
+        ts.check_ids()
+    t = torch.tensor([ms_total, ms_e2e], dtype=torch.float64, device="cuda")
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms_total, ms_e2e = float(t[0]), float(t[1])
+    h2d = sum(x.numel() * x.element_size() for x in host[0])
+    if rank == 0:
+        roof = None
+        if not args.no_kernel_timing:
+            roof = wl.roofline(pkg, st, dev[W:W + min(K, 6)], peaks)
+            if roof is not None:
+                roof.setdefault("peak_source", peak_src)
+        cpu = None
+        if not args.no_cpu_baseline:
+            cpu = BW.run_cpu(wl, steps=3, warmup=1)
+            cpu = {k: cpu[k] for k in ("value", "unit", "cores", "kind", "sample")}
+        per_step = count_own_launches(_StepShim(st), dev[W])
+        line = {"metric": wl.metric, "value": B * world * K / (ms_total * 1e-3), "unit": "samples/s",
+                "n_gpus": world, "steps": K, "warmup": W, "ms_per_step": ms_total / K,
+                "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
+                "data": "synthetic",
+                "config": dict(wl.config(), global_batch=B * world,
+                               l2_flush="distinct batch every step over tables larger than L2"
+                               if args.workload != "fm" else "distinct batch every step (17 GB-class tables)",
+                               parallelism="single" if world == 1 else f"{world} independent replicas "
+                               "(this path does not shard)"),
+                "clocks": clocks,
+                "e2e": {"value": B * world * K / (ms_e2e * 1e-3), "unit": "samples/s",
+                        "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 4, "ms_per_step": ms_e2e / K},
+                "gpu_launches": (per_step or 0) * K * world, "roofline": roof, "cpu_baseline": cpu,
+                "final_loss": float(loss_host[-1])}
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+class _StepShim:
+    def __init__(self, st):
+        self.st = st
+
+    def step(self, *b):
+        return self.st.step(*b)
+
+
 def main():
     args = parse_args()
+    if args.workload != "dlrm":
+        return run_workload_reference(args) if args.impl == "reference" else run_workload(args)
     if args.replicate_max_rows < 0:     # same resolved config for both arms
         world = int(os.environ.get("WORLD_SIZE", str(args.gpus)))
         args.replicate_max_rows = 16384 if world >= 4 else 0

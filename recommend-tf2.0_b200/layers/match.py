@@ -150,7 +150,8 @@ def _ssm_ws(S, D, device):
 
 class _SampledSoftmaxFn(torch.autograd.Function):
     @staticmethod
-    def forward(ctx, weights, biases, labels, inputs, sampled, true_exp, samp_exp, remove_hits, err):
+    def forward(ctx, weights, biases, labels, inputs, sampled, true_exp, samp_exp, remove_hits, err,
+                table=None):
         L.require_cuda(inputs, "sampled_softmax_loss(inputs)")
         weights, inputs = weights.contiguous(), inputs.contiguous()
         B, D = inputs.shape
@@ -166,7 +167,7 @@ class _SampledSoftmaxFn(torch.autograd.Function):
             L.current_stream_ptr())
         L.check(rc, "rtf_sampled_softmax_fwd")
         ctx.save_for_backward(weights, inputs, labels, sampled, true_exp, samp_exp, lse)
-        ctx.biases, ctx.remove_hits = biases, remove_hits
+        ctx.biases, ctx.remove_hits, ctx.table = biases, remove_hits, table
         return loss
 
     @staticmethod
@@ -187,7 +188,15 @@ class _SampledSoftmaxFn(torch.autograd.Function):
             ws.data_ptr(), L.current_stream_ptr())
         L.check(rc, "rtf_sampled_softmax_bwd")
         gw = None
-        if ctx.needs_input_grad[0]:
+        if ctx.table is not None and ctx.table[0].optimizer is not None:
+            # the class-weight matrix is an embedding table with a fused sparse optimizer: its
+            # touched rows ([labels | sampled]) are reduced and updated in place by K2 — no dense
+            # (N, D) gradient is ever materialised
+            tset, t = ctx.table
+            rows = torch.cat([G[:, :1] * inputs, G[:, 1:].t() @ inputs], 0)
+            ids = torch.cat([labels, sampled]).reshape(-1, 1)
+            tset.apply_sparse_grad(ids, [t], rows)
+        elif ctx.needs_input_grad[0]:
             # weight-row gradients: true rows g0*x (B,D), sampled rows G[:,1:]^T x (S,D), reduced
             # per touched row by K2 (deterministic), then placed into a dense (N,D) gradient
             rows = torch.cat([G[:, :1] * inputs, G[:, 1:].t() @ inputs], 0)
@@ -195,15 +204,17 @@ class _SampledSoftmaxFn(torch.autograd.Function):
             keys, tot, _ = embed_bwd([weights], [0], ids, rows, "BF", None, want_unique=True)
             gw = torch.zeros_like(weights)
             gw[keys] = tot[:, :D]
-        return gw, None, None, gx, None, None, None, None, None
+        return gw, None, None, gx, None, None, None, None, None, None
 
 
 def sampled_softmax_loss(weights, biases, labels, inputs, num_sampled, num_classes, num_true=1,
                          sampled_values=None, remove_accidental_hits=True, seed: int = 0,
-                         err: Optional[torch.Tensor] = None):
+                         err: Optional[torch.Tensor] = None, table=None):
     """tf.nn.sampled_softmax_loss (A13).  `sampled_values = (sampled, true_expected_count,
     sampled_expected_count)` may be injected (the only way to reproduce a TF run); otherwise
-    they come from the device log-uniform sampler seeded with `seed`."""
+    they come from the device log-uniform sampler seeded with `seed`.  table=(EmbeddingTables, t):
+    `weights` is table t of that set — with a fused sparse optimizer its touched rows are updated
+    in place by K2 in the backward instead of returning a dense (N, D) gradient."""
     if num_true != 1:
         raise NotImplementedError("num_true != 1")
     labels = labels.reshape(-1).to(torch.int64).contiguous()
@@ -217,7 +228,7 @@ def sampled_softmax_loss(weights, biases, labels, inputs, num_sampled, num_class
         true_exp = true_exp.reshape(-1).to(torch.float32).contiguous()
         samp_exp = samp_exp.reshape(-1).to(torch.float32).contiguous()
     return _SampledSoftmaxFn.apply(weights, biases, labels, inputs, sampled, true_exp, samp_exp,
-                                   remove_accidental_hits, err)
+                                   remove_accidental_hits, err, table)
 
 
 class SampledSoftmaxLayer(Layer):

@@ -169,7 +169,8 @@ class YoutubeDNN(Layer):
                                            optimizer=sparse_optimizer, seed=seed)
         width = user_dnn_hidden_units[-1]
         self.item_table = EmbeddingTables([item_num], [width if conventional else embed_dim],
-                                          optimizer=None, seed=seed)
+                                          optimizer=sparse_optimizer if conventional else None,
+                                          seed=seed)
         self.user_dnn = MatchDNN(user_dnn_hidden_units)
         self.item_dnn = None if conventional else MatchDNN(user_dnn_hidden_units)
         self.sampler_layer = SampledSoftmaxLayer(num_sampled)
@@ -184,9 +185,56 @@ class YoutubeDNN(Layer):
             loss = sampled_softmax_loss(self.item_table.weights[0], None, item_ids, user_out,
                                         self.num_sampled, self.item_num,
                                         sampled_values=sampled_values, seed=self._step,
-                                        err=self.item_table.err)
+                                        err=self.item_table.err, table=(self.item_table, 0))
             return loss.unsqueeze(1)
         item_out = self.item_dnn(self.item_table.lookup(item_ids.reshape(-1, 1)))
         labels = inputs[2]
         return self.sampler_layer([item_out.unsqueeze(1), user_out.unsqueeze(1), labels],
                                   sampled_values=sampled_values)
+
+
+class Trainer:
+    """model.compile(loss, optimizer=Adam(lr)) + one fit step (src/ctr/fm/train.py:49-50,57-64)
+    for any model of this module: embedding tables are updated in place by K2's fused sparse
+    Adam during the backward, every other parameter by one rtf_dense_adam launch (Keras form).
+
+        tr = Trainer(model, loss_fn)          # loss_fn(outputs, labels) -> scalar tensor
+        loss = tr.step(inputs, labels)
+
+    The lazily built layers are created by a no-grad eval forward on the first batch (BatchNorm
+    moving statistics and the tables do not move)."""
+
+    def __init__(self, model: Layer, loss_fn, lr: float = 1e-3, embed_l2: float = 0.0):
+        from .core import DenseAdam
+        self._DenseAdam = DenseAdam
+        self.model, self.loss_fn, self.lr = model, loss_fn, lr
+        self.tables = [m for m in model.modules() if isinstance(m, EmbeddingTables)]
+        for ts in self.tables:
+            if ts.optimizer is None:
+                ts.set_optimizer(SparseOptimizer("adam", lr=lr, l2=embed_l2))
+        self.dense_opt = None
+
+    def _setup(self, inputs):
+        was = self.model.training
+        self.model.eval()
+        with torch.no_grad():
+            self.model(inputs)
+        self.model.train(was)
+        emb = {id(p) for ts in self.tables for p in ts.parameters()}
+        params = [p for p in self.model.parameters() if id(p) not in emb and p.requires_grad]
+        self.dense_opt = self._DenseAdam(params, lr=self.lr)
+
+    def step(self, inputs, labels=None) -> torch.Tensor:
+        if self.dense_opt is None:
+            self._setup(inputs)
+        seen = set()
+        for ts in self.tables:          # one optimizer object may serve several table sets
+            if ts.optimizer is not None and id(ts.optimizer) not in seen:
+                seen.add(id(ts.optimizer))
+                ts.begin_step()
+        out = self.model(inputs)
+        loss = self.loss_fn(out, labels)
+        self.dense_opt.zero_grad()
+        loss.backward()
+        self.dense_opt.step()
+        return loss.detach()
