@@ -336,6 +336,31 @@ int rtf_dense_gemm_tn(const float* d_a, int64_t lda, int64_t stride_a, const flo
                       int64_t stride_d, int M, int N, int K, int batch, void* d_ws, size_t ws_bytes,
                       void* stream);
 
+/* ---- K6: AutoInt interacting layer, fused ---------------------------------------------------
+ * replaces: ctr.layers.modules.MultiHeadAttention.call on a self-attention input X (B, F, dm):
+ *           Q,K,V = act(X W{q,k,v}) (no bias, src/ctr/layers/modules.py:255-270), per-head
+ *           softmax(Q K^T * scale) V with no mask (:211-240), merge heads (:281-283) and, with
+ *           d_w0 != NULL, relu(O + act(X W0)) (:316-323) — ONE launch per direction instead of
+ *           4 tensordots + 2 transposes + 2 batched GEMMs + softmax.
+ * x (B,F,dm), weights (dm, H*hs) row-major, out / gout (B,F,H*hs), all contiguous fp32.
+ * act: 0 none, 1 relu, 2 sigmoid, 3 tanh.  scale: sqrt(hs) is the reference form (:235-237).
+ * _supported: 1 if (F, dm, H, hs) is one of the compiled shapes (F <= 64, H*F <= 128 and
+ *   (dm, H*hs, hs) in {(16,32,16), (32,32,16), (16,16,16), (16,8,8), (8,16,8), (64,64,32)});
+ *   otherwise _fwd/_bwd return RTF_E_RANGE and the caller composes the layer from the
+ *   projection GEMMs + rtf_attn_*.
+ * _bwd: d_out = the forward's output (relu mask of the residual form; may be NULL without W0);
+ *   writes d_gx (B,F,dm) and d_gw (4, dm, H*hs) = dWq|dWk|dWv|dW0 (dW0 zeros without W0), the
+ *   latter reduced over the batch in a fixed order (bit-reproducible).  Workspace: _workspace. */
+int rtf_autoint_layer_supported(int F, int dm, int H, int hs);
+int rtf_autoint_layer_workspace(int64_t B, int dm, int HS, size_t* bytes);
+int rtf_autoint_layer_fwd(const float* d_x, int64_t B, int F, int dm, const float* d_wq,
+                          const float* d_wk, const float* d_wv, const float* d_w0, int H, int hs,
+                          int act, float scale, float* d_out, void* stream);
+int rtf_autoint_layer_bwd(const float* d_x, int64_t B, int F, int dm, const float* d_wq,
+                          const float* d_wk, const float* d_wv, const float* d_w0, int H, int hs,
+                          int act, float scale, const float* d_out, const float* d_gout,
+                          float* d_gx, float* d_gw, void* d_ws, size_t ws_bytes, void* stream);
+
 /* ---- dense optimizer steps (data-parallel replicas) ----------------------------------------
  * replaces: the ResourceApplyAdam that model.compile(optimizer=Adam(learning_rate=1e-3)) runs on
  *           every dense variable (src/ctr/fm/train.py:49-50; Keras form).

@@ -63,6 +63,11 @@ SIGNATURES = {
     "rtf_colsum": [_p, _i64, _p, _i64, _int, _p, _p, _p],
     "rtf_relu_bwd_colsum_workspace": [_i64, _int, C.POINTER(C.c_size_t)],
     "rtf_relu_bwd_colsum": [_p, _p, _i64, _int, _p, _p, _p, _p],
+    "rtf_autoint_layer_supported": [_int, _int, _int, _int],
+    "rtf_autoint_layer_workspace": [_i64, _int, _int, C.POINTER(C.c_size_t)],
+    "rtf_autoint_layer_fwd": [_p, _i64, _int, _int, _p, _p, _p, _p, _int, _int, _int, C.c_float, _p, _p],
+    "rtf_autoint_layer_bwd": [_p, _i64, _int, _int, _p, _p, _p, _p, _int, _int, _int, C.c_float, _p, _p,
+                              _p, _p, _p, C.c_size_t, _p],
     "rtf_dense_adam": [_p, _p, _p, _p, _i64, C.POINTER(rtf_opt), _p],
     "rtf_rows_apply_dense": [_p, _p, _p, _p, _p, _i64, _int, C.POINTER(rtf_opt), _p],
     "rtf_dense_gemm_nn_workspace": [_int, _int, _int, _int, C.POINTER(C.c_size_t)],

@@ -86,6 +86,45 @@ class AttentionLayer(Layer):
                                 _ACT_CODE[self.activation])
 
 
+class _AutoIntLayerFn(torch.autograd.Function):
+    """K6: the whole interacting layer (projections + activation, per-head softmax(QK^T s)V,
+    residual relu) in one launch per direction (csrc/autoint_layer.cu)."""
+
+    @staticmethod
+    def forward(ctx, x, wq, wk, wv, w0, H, hs, act, scale):
+        L.require_cuda(x, "MultiHeadAttention(x)")
+        x = x.contiguous()
+        ws_ = [w.contiguous() for w in (wq, wk, wv)] + [None if w0 is None else w0.contiguous()]
+        B, F, dm = x.shape
+        out = torch.empty((B, F, H * hs), dtype=torch.float32, device=x.device)
+        rc = L.lib().rtf_autoint_layer_fwd(x.data_ptr(), B, F, dm, ws_[0].data_ptr(), ws_[1].data_ptr(),
+                                           ws_[2].data_ptr(), None if w0 is None else ws_[3].data_ptr(),
+                                           H, hs, act, scale, out.data_ptr(), L.current_stream_ptr())
+        L.check(rc, "rtf_autoint_layer_fwd")
+        ctx.save_for_backward(x, ws_[0], ws_[1], ws_[2], ws_[3], out)
+        ctx.cfg = (H, hs, act, scale)
+        return out
+
+    @staticmethod
+    def backward(ctx, gout):
+        x, wq, wk, wv, w0, out = ctx.saved_tensors
+        H, hs, act, scale = ctx.cfg
+        gout = gout.contiguous()
+        B, F, dm = x.shape
+        HS = H * hs
+        gx = torch.empty_like(x)
+        gw = torch.empty((4, dm, HS), dtype=torch.float32, device=x.device)
+        nb = C.c_size_t(0)
+        L.check(L.lib().rtf_autoint_layer_workspace(B, dm, HS, C.byref(nb)), "rtf_autoint_layer_workspace")
+        ws = torch.empty(max(nb.value, 16), dtype=torch.uint8, device=x.device)
+        rc = L.lib().rtf_autoint_layer_bwd(x.data_ptr(), B, F, dm, wq.data_ptr(), wk.data_ptr(),
+                                           wv.data_ptr(), None if w0 is None else w0.data_ptr(), H, hs,
+                                           act, scale, out.data_ptr(), gout.data_ptr(), gx.data_ptr(),
+                                           gw.data_ptr(), ws.data_ptr(), ws.numel(), L.current_stream_ptr())
+        L.check(rc, "rtf_autoint_layer_bwd")
+        return gx, gw[0], gw[1], gw[2], (None if w0 is None else gw[3]), None, None, None, None
+
+
 class MultiHeadAttention(Layer):
     """AutoInt interacting layer: MultiHeadAttention(head_size, head_num=1, l2_reg=l2(1e-4),
     activation='relu', use_res=False, name=''); call(X) or call([q, k, v]) / call([x]).
@@ -101,6 +140,7 @@ class MultiHeadAttention(Layer):
         self._head_num, self._head_size = head_num, head_size
         self._l2_reg = l2(1e-4) if l2_reg is None else l2_reg
         self._activation, self._use_res, self._scale = activation, use_res, scale
+        self.fused = True       # False: always compose from the projection GEMMs + rtf_attn_*
         hs = head_num * head_size
         self.q_dense = Dense(hs, activation=activation, use_bias=False, kernel_regularizer=self._l2_reg)
         self.k_dense = Dense(hs, activation=activation, use_bias=False, kernel_regularizer=self._l2_reg)
@@ -115,9 +155,20 @@ class MultiHeadAttention(Layer):
             ori_q, ori_k, ori_v = (inputs if len(inputs) == 3 else (inputs[0],) * 3)
         else:
             ori_q = ori_k = ori_v = inputs
-        q, k, v = self.q_dense(ori_q), self.k_dense(ori_k), self.v_dense(ori_v)
         hs = self._head_size
         scale = math.sqrt(hs) if self._scale == "reference" else 1.0 / math.sqrt(hs)
+        if (ori_q is ori_k and ori_k is ori_v and ori_q.is_cuda and ori_q.dim() == 3
+                and ori_q.dtype == torch.float32 and self._activation in _ACT_CODE and self.fused
+                and L.lib().rtf_autoint_layer_supported(ori_q.shape[1], ori_q.shape[2], self._head_num, hs)):
+            # K6: self-attention input of a compiled shape -> the whole layer in one launch
+            for dns in (self.q_dense, self.k_dense, self.v_dense, self.res_dense):
+                if dns is not None and not dns._built:
+                    dns.build(tuple(ori_q.shape))
+                    dns._built = True
+            return _AutoIntLayerFn.apply(ori_q, self.q_dense.kernel, self.k_dense.kernel, self.v_dense.kernel,
+                                         self.res_dense.kernel if self._use_res else None, self._head_num,
+                                         hs, _ACT_CODE[self._activation], scale)
+        q, k, v = self.q_dense(ori_q), self.k_dense(ori_k), self.v_dense(ori_v)
         out = attention(q, k, v, self._head_num, scale)
         if self._use_res:
             return torch.relu(out + self.res_dense(ori_v))

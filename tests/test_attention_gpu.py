@@ -163,6 +163,72 @@ def test_ctr_multihead_attention_autoint_layer(rtf, B, F, dm, H, hs, use_res, sc
     assert torch.isfinite(xt.grad).all()
 
 
+def _ctr_mha_fp64(x, Ws, H, hs, act, scale, use_res):
+    """fp64 torch restatement of src/ctr/layers/modules.py:255-270,211-240,281-283,316-323."""
+    f = {"relu": torch.relu, "sigmoid": torch.sigmoid, "tanh": torch.tanh, None: lambda z: z}[act]
+    B, F, _ = x.shape
+    q, k, v = (f(x @ W) for W in Ws[:3])
+    sp = lambda t: t.reshape(B, F, H, hs).transpose(1, 2)                          # noqa: E731
+    div = hs ** -0.5 if scale == "reference" else hs ** 0.5
+    o = (torch.softmax(sp(q) @ sp(k).transpose(-1, -2) / div, -1) @ sp(v)).transpose(1, 2).reshape(B, F, H * hs)
+    return torch.relu(o + f(x @ Ws[3])) if use_res else o
+
+
+@pytest.mark.parametrize("act", ["relu", "sigmoid", "tanh", None])
+@pytest.mark.parametrize("use_res", [False, True])
+@pytest.mark.parametrize("B,F,dm,H,hs", [(37, 39, 16, 2, 16), (300, 39, 32, 2, 16), (9, 64, 16, 1, 16),
+                                         (5, 39, 16, 1, 8), (7, 13, 64, 2, 32), (1, 1, 8, 2, 8)])
+def test_autoint_fused_layer_fwd_bwd_vs_fp64(rtf, B, F, dm, H, hs, use_res, act):
+    """K6 (one launch per direction): output, dX and the four weight gradients against fp64
+    autograd over the reference formula, 1e-5 relative; the fused path must really be taken."""
+    assert rtf.lib().rtf_autoint_layer_supported(F, dm, H, hs) == 1
+    rng = np.random.default_rng(11)
+    x = rng.normal(0, 0.5, (B, F, dm))
+    layer = rtf.layers.ctr.MultiHeadAttention(hs, H, activation=act, use_res=use_res)
+    xt = _t(x, True)
+    out = layer(xt)
+    assert type(out.grad_fn).__name__ == "_AutoIntLayerFnBackward"
+    g = rng.normal(0, 1, (B, F, H * hs))
+    out.backward(_t(g))
+    dens = [layer.q_dense, layer.k_dense, layer.v_dense] + ([layer.res_dense] if use_res else [])
+    Ws = [d.kernel.detach().cpu().double().requires_grad_(True) for d in dens]
+    x64 = torch.from_numpy(x).requires_grad_(True)
+    ref = _ctr_mha_fp64(x64, Ws + ([None] if not use_res else []), H, hs, act, "reference", use_res)
+    ref.backward(torch.from_numpy(g))
+
+    def close(got, want):
+        want = want.detach().numpy()
+        _close(got.detach().cpu().numpy(), want, rtol=1e-5, atol=1e-5 * max(np.abs(want).max(), 1e-30))
+    close(out, ref)
+    close(xt.grad, x64.grad)
+    for d, W in zip(dens, Ws):
+        close(d.kernel.grad, W.grad)
+
+
+def test_autoint_fused_layer_matches_unfused_and_is_deterministic(rtf):
+    rng = np.random.default_rng(5)
+    x = _t(rng.normal(0, 0.5, (513, 39, 16)))
+    fused = rtf.layers.ctr.MultiHeadAttention(16, 2, use_res=True)
+    plain = rtf.layers.ctr.MultiHeadAttention(16, 2, use_res=True)
+    plain.fused = False
+    fused(x), plain(x)
+    for a, b_ in zip(fused.parameters(), plain.parameters()):
+        b_.data.copy_(a.data)
+    g = torch.randn(513, 39, 32, device="cuda")
+    grads = []
+    for layer in (fused, plain, fused):
+        xi = x.clone().requires_grad_(True)
+        for p in layer.parameters():
+            p.grad = None
+        out = layer(xi)
+        out.backward(g)
+        grads.append([out.detach(), xi.grad] + [p.grad.clone() for p in layer.parameters()])
+    for a, b_ in zip(grads[0], grads[1]):
+        torch.testing.assert_close(a, b_, rtol=1e-4, atol=1e-5)
+    for a, b_ in zip(grads[0], grads[2]):                      # fixed reduction order: bit-equal
+        assert torch.equal(a, b_)
+
+
 # ------------------------------------------------------------------ DIN local activation unit (a6)
 @pytest.mark.parametrize("act", ["sigmoid", None, "relu", "tanh"])
 @pytest.mark.parametrize("B,L,d", [(33, 100, 16), (9, 100, 128), (5, 10, 192), (64, 7, 8), (3, 37, 48)])
