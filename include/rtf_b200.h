@@ -361,6 +361,42 @@ int rtf_autoint_layer_bwd(const float* d_x, int64_t B, int F, int dm, const floa
                           int act, float scale, const float* d_out, const float* d_gout,
                           float* d_gx, float* d_gw, void* d_ws, size_t ws_bytes, void* stream);
 
+/* ---- a10: SASRec scoring + loss epilogue, fused with the pos / neg item gathers -------------
+ * replaces: src/match/sasrec/model.py:77-79 (pos / neg Embedding lookups) and :88-96
+ *           (last position, the two dot products, -log sigmoid / -log(1 - sigmoid), concat).
+ * info (B, D) = att_outputs[:, -1] (row stride info_sb); pos ids (B) and neg ids (B, NEG; row
+ * stride neg_sb) index the pos / neg tables (rows, D).  _fwd writes logits (B, 1+NEG) =
+ * [pos | neg] and loss_rows (B) = NEG*(-log s(pos_b)) + sum_j -log(1 - s(neg_bj)); the model's
+ * loss is sum_b loss_rows[b] / (2 B NEG) (finished by rtf_colsum: fixed order).  Out-of-range
+ * ids read as zero rows and set *d_err.
+ * _bwd: d_gloss (device scalar, may be NULL) and d_glogits (B, 1+NEG, may be NULL) are the
+ * incoming gradients; writes d_ginfo (B, D) and d_gemb (B, 1+NEG, D) = ds_bj * info_b, the row
+ * gradients K2 reduces per touched row (pos rows: [:,0,:], neg rows: [:,1:,:]).              */
+int rtf_sasrec_score_fwd(const float* d_info, int64_t info_sb, const float* d_pos_tab,
+                         int64_t pos_rows, const float* d_neg_tab, int64_t neg_rows,
+                         const void* d_pos_ids, const void* d_neg_ids, int ids_i64, int64_t neg_sb,
+                         int64_t B, int NEG, int D, float* d_logits, float* d_loss_rows,
+                         int32_t* d_err, void* stream);
+int rtf_sasrec_score_bwd(const float* d_info, int64_t info_sb, const float* d_pos_tab,
+                         int64_t pos_rows, const float* d_neg_tab, int64_t neg_rows,
+                         const void* d_pos_ids, const void* d_neg_ids, int ids_i64, int64_t neg_sb,
+                         int64_t B, int NEG, int D, const float* d_logits, const float* d_gloss,
+                         const float* d_glogits, float* d_ginfo, float* d_gemb, void* stream);
+
+/* ---- f3: exact top-k inner-product retrieval -------------------------------------------------
+ * replaces: faiss.IndexFlatIP(d).add(item_embs); D, I = index.search(user_embs, k)
+ *           (src/match/fm/train.py:71-75, src/match/dssm/dssm_train.py:74-78).
+ * users (B, D) row stride u_ld, items (N, D) row stride i_ld, fp32; for every user the k
+ * (<= 16) items of largest inner product, best first: out_idx (B, k) int64 (-1 past N),
+ * out_score (B, k) = the fp64-accumulated score rounded to fp32.  Ties: lower index first.
+ * Scores come from the fp32-accurate tensor-core GEMM, the best 32 per row are re-scored in
+ * fp64; bit 0 of *d_flag (caller zeroes it) is set if a row's result could not be PROVEN equal
+ * to the fp64 ranking (more than 32 - k near-ties).  D % 4 == 0, N < 2^31 - 1.               */
+int rtf_topk_ip_workspace(int64_t B, int64_t N, int D, int k, size_t* bytes);
+int rtf_topk_ip(const float* d_users, int64_t u_ld, int64_t B, const float* d_items, int64_t i_ld,
+                int64_t N, int D, int k, int64_t* d_out_idx, float* d_out_score, int32_t* d_flag,
+                void* d_ws, size_t ws_bytes, void* stream);
+
 /* ---- dense optimizer steps (data-parallel replicas) ----------------------------------------
  * replaces: the ResourceApplyAdam that model.compile(optimizer=Adam(learning_rate=1e-3)) runs on
  *           every dense variable (src/ctr/fm/train.py:49-50; Keras form).

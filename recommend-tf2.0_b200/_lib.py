@@ -68,6 +68,11 @@ SIGNATURES = {
     "rtf_autoint_layer_fwd": [_p, _i64, _int, _int, _p, _p, _p, _p, _int, _int, _int, C.c_float, _p, _p],
     "rtf_autoint_layer_bwd": [_p, _i64, _int, _int, _p, _p, _p, _p, _int, _int, _int, C.c_float, _p, _p,
                               _p, _p, _p, C.c_size_t, _p],
+    "rtf_sasrec_score_fwd": [_p, _i64, _p, _i64, _p, _i64, _p, _p, _int, _i64, _i64, _int, _int, _p, _p, _p, _p],
+    "rtf_sasrec_score_bwd": [_p, _i64, _p, _i64, _p, _i64, _p, _p, _int, _i64, _i64, _int, _int, _p, _p, _p,
+                             _p, _p, _p],
+    "rtf_topk_ip_workspace": [_i64, _i64, _int, _int, C.POINTER(C.c_size_t)],
+    "rtf_topk_ip": [_p, _i64, _i64, _p, _i64, _i64, _int, _int, _p, _p, _p, _p, C.c_size_t, _p],
     "rtf_dense_adam": [_p, _p, _p, _p, _i64, C.POINTER(rtf_opt), _p],
     "rtf_rows_apply_dense": [_p, _p, _p, _p, _p, _i64, _int, C.POINTER(rtf_opt), _p],
     "rtf_dense_gemm_nn_workspace": [_int, _int, _int, _int, C.POINTER(C.c_size_t)],

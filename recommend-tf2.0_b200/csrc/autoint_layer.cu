@@ -80,19 +80,23 @@ __device__ __forceinline__ void ai_project(const float* __restrict__ Xs, float* 
     const int c = lane + 32 * cc;
     if (c >= HS) continue;
     float* dst = Ms + m * kMat + c;
-#pragma unroll 2
-    for (int r = 0; r < F; ++r) {
-      const float4* xr = reinterpret_cast<const float4*>(Xs + r * DM);
-      float acc = 0.f;
+    for (int r0 = 0; r0 < F; r0 += 4) {   // 4 independent accumulation chains
+      float acc[4] = {0.f, 0.f, 0.f, 0.f};
 #pragma unroll
       for (int k4 = 0; k4 < DM / 4; ++k4) {
-        const float4 xv = xr[k4];
-        acc = fmaf(xv.x, wreg[cc][4 * k4 + 0], acc);
-        acc = fmaf(xv.y, wreg[cc][4 * k4 + 1], acc);
-        acc = fmaf(xv.z, wreg[cc][4 * k4 + 2], acc);
-        acc = fmaf(xv.w, wreg[cc][4 * k4 + 3], acc);
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+          const int r = min(r0 + u, F - 1);
+          const float4 xv = *reinterpret_cast<const float4*>(Xs + r * DM + 4 * k4);
+          acc[u] = fmaf(xv.x, wreg[cc][4 * k4 + 0], acc[u]);
+          acc[u] = fmaf(xv.y, wreg[cc][4 * k4 + 1], acc[u]);
+          acc[u] = fmaf(xv.z, wreg[cc][4 * k4 + 2], acc[u]);
+          acc[u] = fmaf(xv.w, wreg[cc][4 * k4 + 3], acc[u]);
+        }
       }
-      dst[r * HS] = ai_act(act, acc);
+#pragma unroll
+      for (int u = 0; u < 4; ++u)
+        if (r0 + u < F) dst[(r0 + u) * HS] = ai_act(act, acc[u]);
     }
   }
 }
@@ -112,20 +116,27 @@ __device__ __forceinline__ void ai_scores(const float* __restrict__ Ms, float* _
   }
   float* prow = Ps + (h * F + i) * kS;
   float mx = -INFINITY;
-  for (int j = 0; j < F; ++j) {
-    const float4* kr = reinterpret_cast<const float4*>(K + j * HS + h * HSZ);
-    float s = 0.f;
+  for (int j0 = 0; j0 < F; j0 += 4) {     // 4 independent dot products
+    float s4[4] = {0.f, 0.f, 0.f, 0.f};
 #pragma unroll
     for (int d4 = 0; d4 < HSZ / 4; ++d4) {
-      const float4 kv = kr[d4];
-      s = fmaf(q[4 * d4], kv.x, s);
-      s = fmaf(q[4 * d4 + 1], kv.y, s);
-      s = fmaf(q[4 * d4 + 2], kv.z, s);
-      s = fmaf(q[4 * d4 + 3], kv.w, s);
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        const int j = min(j0 + u, F - 1);
+        const float4 kv = *reinterpret_cast<const float4*>(K + j * HS + h * HSZ + 4 * d4);
+        s4[u] = fmaf(q[4 * d4], kv.x, s4[u]);
+        s4[u] = fmaf(q[4 * d4 + 1], kv.y, s4[u]);
+        s4[u] = fmaf(q[4 * d4 + 2], kv.z, s4[u]);
+        s4[u] = fmaf(q[4 * d4 + 3], kv.w, s4[u]);
+      }
     }
-    s *= scale;
-    prow[j] = s;
-    mx = fmaxf(mx, s);
+#pragma unroll
+    for (int u = 0; u < 4; ++u)
+      if (j0 + u < F) {
+        const float s = s4[u] * scale;
+        prow[j0 + u] = s;
+        mx = fmaxf(mx, s);
+      }
   }
   float sum = 0.f;
   for (int j = 0; j < F; ++j) {
@@ -269,19 +280,26 @@ autoint_bwd_kernel(const __grid_constant__ AiParams P) {
         go[4 * d4] = t.x; go[4 * d4 + 1] = t.y; go[4 * d4 + 2] = t.z; go[4 * d4 + 3] = t.w;
       }
       float delta = 0.f;
-      for (int j = 0; j < F; ++j) {
-        const float4* vr = reinterpret_cast<const float4*>(V + j * HS);
-        float dp = 0.f;
+      for (int j0 = 0; j0 < F; j0 += 4) {
+        float dp4[4] = {0.f, 0.f, 0.f, 0.f};
 #pragma unroll
         for (int d4 = 0; d4 < HSZ / 4; ++d4) {
-          const float4 vv = vr[d4];
-          dp = fmaf(go[4 * d4], vv.x, dp);
-          dp = fmaf(go[4 * d4 + 1], vv.y, dp);
-          dp = fmaf(go[4 * d4 + 2], vv.z, dp);
-          dp = fmaf(go[4 * d4 + 3], vv.w, dp);
+#pragma unroll
+          for (int u = 0; u < 4; ++u) {
+            const int j = min(j0 + u, F - 1);
+            const float4 vv = *reinterpret_cast<const float4*>(V + j * HS + 4 * d4);
+            dp4[u] = fmaf(go[4 * d4], vv.x, dp4[u]);
+            dp4[u] = fmaf(go[4 * d4 + 1], vv.y, dp4[u]);
+            dp4[u] = fmaf(go[4 * d4 + 2], vv.z, dp4[u]);
+            dp4[u] = fmaf(go[4 * d4 + 3], vv.w, dp4[u]);
+          }
         }
-        dsrow[j] = dp;
-        delta = fmaf(prow[j], dp, delta);
+#pragma unroll
+        for (int u = 0; u < 4; ++u)
+          if (j0 + u < F) {
+            dsrow[j0 + u] = dp4[u];
+            delta = fmaf(prow[j0 + u], dp4[u], delta);
+          }
       }
 #pragma unroll
       for (int d = 0; d < HSZ; ++d) dq[d] = 0.f;

@@ -119,6 +119,67 @@ class DIN(Layer):
         return torch.sigmoid(self.final_output(self.dropout(x)))
 
 
+class _SasrecScoreFn(torch.autograd.Function):
+    """a10 epilogue (csrc/sasrec_score.cu): pos / neg gathers + dot scores + the log loss in one
+    launch; backward re-gathers, returns d seq_info and hands the row gradients to K2."""
+
+    @staticmethod
+    def forward(ctx, tset: EmbeddingTables, info, pos, neg, pos_t, neg_t, *weights):
+        import ctypes as C
+        from . import _lib as L
+        from .fm import colsum
+        L.require_cuda(info, "SASRec scores(seq_info)")
+        info = info.contiguous()
+        pos, neg = pos.reshape(-1).contiguous(), neg.contiguous()
+        if pos.dtype != neg.dtype:
+            neg = neg.to(pos.dtype)
+        B, D = info.shape
+        NEG = neg.shape[1]
+        Wp, Wn = weights[pos_t], weights[neg_t]
+        logits = torch.empty((B, 1 + NEG), dtype=torch.float32, device=info.device)
+        rows = torch.empty((B, 1), dtype=torch.float32, device=info.device)
+        rc = L.lib().rtf_sasrec_score_fwd(info.data_ptr(), info.stride(0), Wp.data_ptr(), Wp.shape[0],
+                                          Wn.data_ptr(), Wn.shape[0], pos.data_ptr(), neg.data_ptr(),
+                                          int(pos.dtype == torch.int64), neg.stride(0), B, NEG, D,
+                                          logits.data_ptr(), rows.data_ptr(), tset.err.data_ptr(),
+                                          L.current_stream_ptr())
+        L.check(rc, "rtf_sasrec_score_fwd")
+        loss = colsum(rows).reshape(()) / (2.0 * B * NEG)
+        ctx.tset, ctx.tabs = tset, (pos_t, neg_t)
+        ctx.save_for_backward(info, pos, neg, logits)
+        return logits, loss
+
+    @staticmethod
+    def backward(ctx, glogits, gloss):
+        from . import _lib as L
+        info, pos, neg, logits = ctx.saved_tensors
+        tset, (pos_t, neg_t) = ctx.tset, ctx.tabs
+        Wp, Wn = tset.weights[pos_t], tset.weights[neg_t]
+        B, D = info.shape
+        NEG = neg.shape[1]
+        ginfo = torch.empty_like(info)
+        gemb = torch.empty((B, 1 + NEG, D), dtype=torch.float32, device=info.device)
+        gl = None if gloss is None else gloss.reshape(1).to(torch.float32).contiguous()
+        gg = None if glogits is None else glogits.contiguous()
+        rc = L.lib().rtf_sasrec_score_bwd(info.data_ptr(), info.stride(0), Wp.data_ptr(), Wp.shape[0],
+                                          Wn.data_ptr(), Wn.shape[0], pos.data_ptr(), neg.data_ptr(),
+                                          int(pos.dtype == torch.int64), neg.stride(0), B, NEG, D,
+                                          logits.data_ptr(), None if gl is None else gl.data_ptr(),
+                                          None if gg is None else gg.data_ptr(), ginfo.data_ptr(),
+                                          gemb.data_ptr(), L.current_stream_ptr())
+        L.check(rc, "rtf_sasrec_score_bwd")
+        # row gradients -> K2 (fused sparse optimizer, or sparse COO gradients per table)
+        nw = len(tset.weights)
+        g_pos = tset.grads_from_lookup_grad(pos.reshape(B, 1), (pos_t,), gemb[:, 0, :], "BL", None)
+        g_neg = tset.grads_from_lookup_grad(neg, (neg_t,), gemb[:, 1:, :], "BL", None)
+        wg = [None] * nw
+        for g in (g_pos, g_neg):
+            for t in range(nw):
+                if g[t] is not None:
+                    wg[t] = g[t] if wg[t] is None else wg[t] + g[t]
+        return (None, ginfo, None, None, None, None) + tuple(wg)
+
+
 class SASRec(Layer):
     """src/match/sasrec/model.py:19-97: three separate tables (seq/pos/neg item, :75-79), no
     positional embedding (:74), x *= mask before and after every block (:82,86), last position,
@@ -129,6 +190,7 @@ class SASRec(Layer):
                  sparse_optimizer: Optional[SparseOptimizer] = None, seed=None):
         super().__init__()
         self.seq_len, self.neg_len, self.embed_dim = seq_len, neg_len, embed_dim
+        self.fused_scores = True    # False: separate lookups + framework elementwise tail
         self.tables = EmbeddingTables([item_num] * 3, [embed_dim] * 3, "random_uniform",
                                       optimizer=sparse_optimizer, seed=seed)
         self.encoder_layer = torch.nn.ModuleList(
@@ -139,12 +201,16 @@ class SASRec(Layer):
         seq, pos, neg = (_as_int_ids(t) for t in inputs)     # (B,L), (B,1), (B,neg_len)
         mask = (seq != 0).to(torch.float32).unsqueeze(-1)                       # :72
         seq_embed = self.tables.lookup(seq, (0,), "BL")                         # (B,L,D)
-        pos_embed = self.tables.lookup(pos, (1,), "BL")
-        neg_embed = self.tables.lookup(neg, (2,), "BL")
         att_outputs = seq_embed * mask                                          # :81-82
         for block in self.encoder_layer:
             att_outputs = block([att_outputs, mask])
             att_outputs = att_outputs * mask                                    # :86
+        if self.fused_scores:
+            # :77-79 + :88-96 in one launch (the pos / neg rows never round-trip HBM)
+            return _SasrecScoreFn.apply(self.tables, att_outputs[:, -1, :], pos, neg, 1, 2,
+                                        *self.tables.weights)
+        pos_embed = self.tables.lookup(pos, (1,), "BL")
+        neg_embed = self.tables.lookup(neg, (2,), "BL")
         seq_info = att_outputs[:, -1:, :]                                       # :88
         pos_scores = (seq_info * pos_embed).sum(-1)
         neg_scores = (seq_info * neg_embed).sum(-1)

@@ -379,6 +379,63 @@ def test_sasrec_tail_matches_oracle(rtf):
     _close(float(loss), want_loss, rtol=1e-5)
 
 
+@pytest.mark.parametrize("B,NEG,D,N", [(5, 7, 16, 50), (33, 100, 64, 1000), (2, 1, 8, 3), (16, 100, 128, 40)])
+def test_sasrec_score_kernel_vs_oracle_fwd_bwd(rtf, B, NEG, D, N):
+    """a10 epilogue kernel (gathers + dots + log loss): logits / loss vs the oracle
+    (src/match/sasrec/model.py:88-96), d seq_info and the per-table row gradients vs fp64
+    autograd over the same formula (duplicate ids included: K2 sums them)."""
+    from recommend_tf2_b200.models import _SasrecScoreFn
+    rng = np.random.default_rng(8)
+    tabs = [rng.normal(0, 0.5, (N, D)).astype(np.float32) for _ in range(3)]
+    info = rng.normal(0, 0.5, (B, D)).astype(np.float32)
+    pos = rng.integers(0, N, (B, 1))
+    neg = rng.integers(0, N, (B, NEG))
+    ts = rtf.EmbeddingTables.from_tensors([_t(t) for t in tabs])
+    for w in ts.weights:
+        w.requires_grad_(True)
+    it = _t(info, True)
+    logits, loss = _SasrecScoreFn.apply(ts, it, _t(pos).to(torch.int32), _t(neg).to(torch.int32), 1, 2,
+                                        *ts.weights)
+    att = info[:, None, :].astype(np.float64)
+    want_logits, want_loss = OA.sasrec_scores_loss(att, tabs[1][pos].astype(np.float64),
+                                                   tabs[2][neg].astype(np.float64))
+    _close(logits.detach().cpu().numpy(), want_logits, rtol=1e-5, atol=1e-5 * np.abs(want_logits).max())
+    _close(float(loss), want_loss, rtol=1e-5)
+    gl = rng.normal(0, 1, (B, 1 + NEG))
+    (loss * 3.0 + (logits * _t(gl)).sum()).backward()
+    i64 = torch.from_numpy(info).double().requires_grad_(True)
+    T64 = [torch.from_numpy(t).double().requires_grad_(True) for t in tabs]
+    pe, ne = T64[1][torch.from_numpy(pos)], T64[2][torch.from_numpy(neg)]
+    ps, ns = (i64[:, None, :] * pe).sum(-1), (i64[:, None, :] * ne).sum(-1)
+    l64 = (-torch.log(torch.sigmoid(ps)) - torch.log(1 - torch.sigmoid(ns))).mean() / 2
+    (l64 * 3.0 + (torch.cat([ps, ns], -1) * torch.from_numpy(gl)).sum()).backward()
+    w = i64.grad.numpy()
+    _close(it.grad.cpu().numpy(), w, rtol=1e-5, atol=1e-5 * np.abs(w).max())
+    for t in (1, 2):
+        w = T64[t].grad.numpy()
+        _close(ts.weights[t].grad.to_dense().cpu().numpy(), w, rtol=1e-5, atol=1e-5 * np.abs(w).max())
+    assert ts.weights[0].grad is None
+
+
+def test_sasrec_fused_scores_match_unfused_training(rtf):
+    from recommend_tf2_b200.models import SASRec
+    seq = torch.randint(1, 100, (8, 10), device="cuda", dtype=torch.int32)
+    seq[:, :4] = 0
+    pos = torch.randint(1, 100, (8, 1), device="cuda", dtype=torch.int32)
+    neg = torch.randint(1, 100, (8, 100), device="cuda", dtype=torch.int32)
+    outs = []
+    for fused in (True, False):
+        m = SASRec(item_num=100, embed_dim=64, blocks=2, seq_len=10, neg_len=100, seed=0)
+        m.fused_scores = fused
+        torch.manual_seed(0)
+        tr = rtf.models.Trainer(m, lambda out, y: out[1], lr=1e-2)
+        losses = [float(tr.step([seq, pos, neg])) for _ in range(3)]
+        outs.append((losses, [w.detach().clone() for w in m.tables.weights]))
+    np.testing.assert_allclose(outs[0][0], outs[1][0], rtol=1e-5)
+    for a, b_ in zip(outs[0][1], outs[1][1]):
+        torch.testing.assert_close(a, b_, rtol=1e-4, atol=1e-6)
+
+
 def test_dice_pooling_and_models_smoke(rtf):
     x = torch.randn(64, 40, device="cuda")
     dice = rtf.layers.Dice()
