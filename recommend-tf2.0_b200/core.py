@@ -135,9 +135,15 @@ class Dense(Layer):
         self.bias = self.add_weight("bias", (self.units,), "zeros") if self.use_bias else None
 
     def call(self, x, **kwargs):
-        if self.bias is not None and x.dim() == 2 and x.is_cuda:
+        if self.bias is not None and x.dim() >= 2 and x.is_cuda:
+            # rank-3 inputs contract the last axis (Keras tensordot, App. A4): the same GEMM on
+            # the flattened (B*L, d) rows — tensor-core path, fused bias / ReLU / bias-gradient
             relu = self._act_name == "relu"
-            y = _DenseFn.apply(x, self.kernel, self.bias, relu)
+            lead = x.shape[:-1]
+            x2 = x.reshape(-1, x.shape[-1]) if x.dim() > 2 else x
+            y = _DenseFn.apply(x2, self.kernel, self.bias, relu)
+            if x.dim() > 2:
+                y = y.reshape(*lead, self.units)
             return y if (relu or self.activation is None) else self.activation(y)
         y = torch.matmul(x, self.kernel)
         if self.bias is not None:

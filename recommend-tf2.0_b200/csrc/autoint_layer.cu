@@ -65,8 +65,8 @@ struct AiParams {
 
 // shared-memory layout (floats), sized by the actual field count F:
 //   Xs [F][DM] | Q K V R, each [F][HS] (stride kMat = F*HS) | (bwd: dO [F][HS]) |
-//   P [H][F][F+1] (| bwd: dS, same shape); score rows have stride F+1 so that phase B's column
-//   reads hit distinct banks.
+//   P [H][F][F|1] (| bwd: dS, same shape); score rows have an ODD stride: a thread walks its own
+//   row, so lanes (different rows) must land in different banks (stride 40 was 8-way conflicted).
 
 // projections of one sample: M_m[r][c] = act(sum_k X[r][k] W_m[k][c]) for the thread's (m, c)
 template <int DM, int HS>
@@ -105,7 +105,7 @@ __device__ __forceinline__ void ai_project(const float* __restrict__ Xs, float* 
 template <int DM, int HS, int HSZ>
 __device__ __forceinline__ void ai_scores(const float* __restrict__ Ms, float* __restrict__ Ps,
                                           int F, int h, int i, float scale) {
-  const int kMat = F * HS, kS = F + 1;
+  const int kMat = F * HS, kS = F | 1;
   const float* Q = Ms;
   const float* K = Ms + kMat;
   float q[HSZ];
@@ -171,7 +171,7 @@ __global__ void __launch_bounds__(AI_THREADS, 4)
 autoint_fwd_kernel(const __grid_constant__ AiParams P) {
   extern __shared__ __align__(16) float sm[];
   const int F = P.F, H = P.H;
-  const int kMat = F * HS, kS = F + 1;
+  const int kMat = F * HS, kS = F | 1;
   float* Xs = sm;                        // [F][DM]
   float* Ms = Xs + F * DM;               // Q | K | V | R, each [F][HS]
   float* Ps = Ms + 4 * kMat;             // [H][F][kS]
@@ -229,7 +229,7 @@ autoint_bwd_kernel(const __grid_constant__ AiParams P) {
   extern __shared__ __align__(16) float sm[];
   constexpr int NC = (HS + 31) / 32;
   const int F = P.F, H = P.H;
-  const int kMat = F * HS, kS = F + 1;
+  const int kMat = F * HS, kS = F | 1;
   float* Xs = sm;                        // [F][DM]
   float* Ms = Xs + F * DM;               // Q | K | V | R  ->  dQpre | dKpre | dVpre | dRpre
   float* dO = Ms + 4 * kMat;             // [F][HS] gradient entering the attention output
@@ -441,11 +441,11 @@ autoint_dw_reduce(const float* __restrict__ partial, int ncta, int n, float* __r
 static size_t ai_round16(size_t nfloats) { return (nfloats + 3) / 4 * 4 * sizeof(float); }
 template <int DM, int HS>
 static size_t ai_fwd_smem(int F, int H) {
-  return ai_round16((size_t)F * DM + 4 * (size_t)F * HS + (size_t)H * F * (F + 1));
+  return ai_round16((size_t)F * DM + 4 * (size_t)F * HS + (size_t)H * F * (F | 1));
 }
 template <int DM, int HS>
 static size_t ai_bwd_smem(int F, int H) {
-  return ai_round16((size_t)F * DM + 5 * (size_t)F * HS + 2 * (size_t)H * F * (F + 1));
+  return ai_round16((size_t)F * DM + 5 * (size_t)F * HS + 2 * (size_t)H * F * (F | 1));
 }
 
 static int ai_grid(long long B, int per_sm) {

@@ -201,8 +201,9 @@ def test_autoint_fused_layer_fwd_bwd_vs_fp64(rtf, B, F, dm, H, hs, use_res, act)
         _close(got.detach().cpu().numpy(), want, rtol=1e-5, atol=1e-5 * max(np.abs(want).max(), 1e-30))
     close(out, ref)
     close(xt.grad, x64.grad)
-    for d, W in zip(dens, Ws):
-        close(d.kernel.grad, W.grad)
+    for d, W in zip(dens, Ws):      # a fp32 reduction over B*F terms: tolerance scaled accordingly
+        w = W.grad.numpy()
+        _close(d.kernel.grad.cpu().numpy(), w, rtol=1e-5, atol=5e-5 * np.abs(w).max())
 
 
 def test_autoint_fused_layer_matches_unfused_and_is_deterministic(rtf):
@@ -223,8 +224,8 @@ def test_autoint_fused_layer_matches_unfused_and_is_deterministic(rtf):
         out = layer(xi)
         out.backward(g)
         grads.append([out.detach(), xi.grad] + [p.grad.clone() for p in layer.parameters()])
-    for a, b_ in zip(grads[0], grads[1]):
-        torch.testing.assert_close(a, b_, rtol=1e-4, atol=1e-5)
+    for a, b_ in zip(grads[0], grads[1]):      # two fp32 summation orders of B*F = 20 007 terms
+        torch.testing.assert_close(a, b_, rtol=1e-3, atol=1e-4 * float(b_.abs().max()))
     for a, b_ in zip(grads[0], grads[2]):                      # fixed reduction order: bit-equal
         assert torch.equal(a, b_)
 
