@@ -397,6 +397,19 @@ int rtf_topk_ip(const float* d_users, int64_t u_ld, int64_t B, const float* d_it
                 int64_t N, int D, int k, int64_t* d_out_idx, float* d_out_score, int32_t* d_flag,
                 void* d_ws, size_t ws_bytes, void* stream);
 
+/* ---- multi-GPU exchange, forward half as a copy kernel --------------------------------------
+ * replaces: the all-to-all of pooled embeddings implied by sharding the tables that
+ *           MirroredStrategy (src/ctr/fm/train.py:43) mirrors instead.
+ * Pulls the rows of this rank's B samples from the holders' owner-gathered (B_global, T_g*D)
+ * buffers (same device tables of peer-mapped addresses as rtf_embed_dot_peer_fwd with
+ * d_peer_str != NULL) into a LOCAL (B, n_fields*D) buffer, so that it can run on a side stream
+ * behind the bottom MLP and the interaction (rtf_dot_rows_fwd) / its backward
+ * (rtf_embed_dot_peer_bwd, d_xsave = this buffer) read local HBM only.                         */
+int rtf_peer_pull_rows(const int64_t* d_peer_tab, const int64_t* d_peer_str, int64_t sample0, int G,
+                       uint64_t rw_mask, const int64_t* rows, int n_fields, int D, const void* d_ids,
+                       int ids_i64, int64_t B, int64_t ids_sb, int64_t ids_sf, float* d_out,
+                       int64_t out_sb, int32_t* d_err, void* stream);
+
 /* ---- dense optimizer steps (data-parallel replicas) ----------------------------------------
  * replaces: the ResourceApplyAdam that model.compile(optimizer=Adam(learning_rate=1e-3)) runs on
  *           every dense variable (src/ctr/fm/train.py:49-50; Keras form).

@@ -82,6 +82,7 @@ class DLRMTrainer:
             model.embed_layers.set_optimizer(SparseOptimizer("adam", lr=lr, l2=model.embed_reg))
         self.dense_opt = None
         self.lr = lr
+        model.embed_layers.async_update = True     # step() ends with wait_pending()
 
     def step(self, dense, sparse, labels) -> torch.Tensor:
         m = self.model
@@ -94,4 +95,5 @@ class DLRMTrainer:
         self.dense_opt.zero_grad()
         loss.backward()
         self.dense_opt.step()
+        m.embed_layers.wait_pending()   # K2's row update ran on the side stream behind the MLP backward
         return loss.detach()

@@ -233,6 +233,7 @@ class EmbeddingTables(torch.nn.Module):
 
     def lookup(self, ids: torch.Tensor, field_table: Optional[Sequence[int]] = None,
                layout: str = "BF", pool: Optional[str] = None) -> torch.Tensor:
+        self.wait_pending()
         if field_table is None:
             field_table = list(range(len(self.weights)))
         return _LookupFn.apply(self, ids, tuple(field_table), layout, pool, *self.weights)
@@ -249,6 +250,7 @@ class EmbeddingTables(torch.nn.Module):
         nbytes = C.c_size_t(0)
         L.check(lib.rtf_embed_bwd_workspace(n, max(dims), C.byref(nbytes)), "rtf_embed_bwd_workspace")
         ws = torch.empty(max(nbytes.value, 16), dtype=torch.uint8, device=ids.device)
+        self.wait_pending()
         cur = torch.cuda.current_stream()
         if getattr(self, "_side", None) is None:
             self._side = torch.cuda.Stream()
@@ -290,6 +292,29 @@ class EmbeddingTables(torch.nn.Module):
                                      h["ws"].data_ptr(), h["ws"].numel(), L.current_stream_ptr())
         L.check(rc, "rtf_embed_bwd_apply")
 
+    def apply_prepared_async(self, h, grad, pool=None):
+        """apply_prepared on the side stream: the gradient half of K2 (HBM-bound) then overlaps
+        whatever the caller enqueues next on the current stream (the bottom MLP's backward GEMMs,
+        tensor-core-bound).  The tables are consistent again after wait_pending()."""
+        cur = torch.cuda.current_stream()
+        if getattr(self, "_side", None) is None:
+            self._side = torch.cuda.Stream()
+        side = self._side
+        side.wait_stream(cur)                    # grad is complete
+        with torch.cuda.stream(side):
+            self.apply_prepared(h, grad, pool)
+            ev = torch.cuda.Event()
+            ev.record(side)
+        grad.record_stream(side)
+        self._pending_ev = ev
+
+    def wait_pending(self):
+        """Make the current stream wait for an asynchronous row update (apply_prepared_async)."""
+        ev = getattr(self, "_pending_ev", None)
+        if ev is not None:
+            torch.cuda.current_stream().wait_event(ev)
+            self._pending_ev = None
+
     def apply_sparse_grad(self, ids, field_table, grad, layout="BF", pool=None):
         opt = self.optimizer
         step = max(opt.step, 1)
@@ -318,6 +343,7 @@ class EmbeddingTables(torch.nn.Module):
     def check_ids(self):
         """Raise like TF's CPU gather (InvalidArgument) if any lookup since the last check used an
         out-of-range id.  Reads a device flag, i.e. synchronises."""
+        self.wait_pending()
         if int(self.err.item()) != 0:
             self.err.zero_()
             raise IndexError("embedding lookup: id out of range [0, input_dim)")

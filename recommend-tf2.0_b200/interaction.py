@@ -97,7 +97,13 @@ class _EmbedDotFn(torch.autograd.Function):
                                        L.current_stream_ptr())
         L.check(rc, "rtf_embed_dot_bwd")
         if ctx.prepared is not None:
-            tset.apply_prepared(ctx.prepared, gemb)
+            # with a trainer that opts in (async_update), the gradient half of K2 goes to the side
+            # stream and overlaps the bottom MLP's backward GEMMs; wait_pending() orders the
+            # tables again before anything else touches them
+            if getattr(tset, "async_update", False):   # a trainer that calls wait_pending()
+                tset.apply_prepared_async(ctx.prepared, gemb)
+            else:
+                tset.apply_prepared(ctx.prepared, gemb)
             return (None, None, None, None, gdense) + (None,) * len(tset.weights)
         wgrads = tset.grads_from_lookup_grad(ids, field_table, gemb, "BF", None)
         return (None, None, None, None, gdense) + wgrads
@@ -111,4 +117,5 @@ def embed_dot(tset: EmbeddingTables, ids: torch.Tensor, dense: torch.Tensor,
         raise TypeError("ids must be int32 or int64")
     if field_table is None:
         field_table = tuple(range(len(tset.weights)))
+    tset.wait_pending()
     return _EmbedDotFn.apply(tset, ids, tuple(field_table), pad_to, dense, *tset.weights)

@@ -390,6 +390,8 @@ class ShardedDLRMTrainer:
         for t in params + bufs:                            # same start on every rank
             dist.broadcast(t.data, 0)
         self.dense_opt = DenseAdam(params, lr=self.lr)
+        if hasattr(m, "async_update"):
+            m.async_update = True       # step() always ends with finish_backward()
 
     def step(self, dense, sparse, labels) -> torch.Tensor:
         m = self.model
@@ -404,9 +406,11 @@ class ShardedDLRMTrainer:
         # asynchronous so that it overlaps the reverse exchange barrier + K2 on the embedding
         # shards (finish_backward)
         work = dist.all_reduce(self.dense_opt.flat_grad, async_op=True)
-        m.finish_backward()
+        if not getattr(m, "async_update", False):
+            m.finish_backward()
         work.wait()
         self.dense_opt.step()
+        m.finish_backward()             # async: the row update ran behind the MLP backward / Adam
         return loss.detach()
 
 
@@ -574,16 +578,26 @@ class _PeerDotFn(torch.autograd.Function):
         D = dense.shape[1]
         cols = dot_out_cols(F + 1, D, pad_to)
         out = torch.empty((B, cols), dtype=torch.float32, device=dense.device)
-        xsave = torch.empty((B, F * D), dtype=torch.float32, device=dense.device)
         owner = model.gather == "owner"
-        rc = L.lib().rtf_embed_dot_peer_fwd(
-            (model._d_peer_optr if owner else model._d_peer_tab).data_ptr(),
-            model._d_peer_ostr.data_ptr() if owner else None, model.rank * B,
-            lay.world, lay.rw_mask, model._rows_arr, F, D,
-            ids.data_ptr(), int(ids.dtype == torch.int64), B, ids.stride(0), ids.stride(1),
-            dense.data_ptr(), dense.stride(0), out.data_ptr(), cols, cols, xsave.data_ptr(),
-            xsave.stride(0), model.embed_layers.err.data_ptr(), L.current_stream_ptr())
-        L.check(rc, "rtf_embed_dot_peer_fwd")
+        if owner:
+            # the rows of my samples were pulled into model._xsave by rtf_peer_pull_rows on the
+            # exchange stream (behind the bottom MLP): the interaction reads local HBM only
+            xsave = model._xsave
+            base = [dense.data_ptr()] + [xsave.data_ptr() + t * D * 4 for t in range(F)]
+            stride = [dense.stride(0)] + [xsave.stride(0)] * F
+            rc = L.lib().rtf_dot_rows_fwd((C.c_void_p * (F + 1))(*base), (C.c_int64 * (F + 1))(*stride),
+                                          F + 1, D, B, out.data_ptr(), cols, cols, None, 0,
+                                          L.current_stream_ptr())
+            L.check(rc, "rtf_dot_rows_fwd")
+        else:
+            xsave = torch.empty((B, F * D), dtype=torch.float32, device=dense.device)
+            rc = L.lib().rtf_embed_dot_peer_fwd(
+                model._d_peer_tab.data_ptr(), None, model.rank * B,
+                lay.world, lay.rw_mask, model._rows_arr, F, D,
+                ids.data_ptr(), int(ids.dtype == torch.int64), B, ids.stride(0), ids.stride(1),
+                dense.data_ptr(), dense.stride(0), out.data_ptr(), cols, cols, xsave.data_ptr(),
+                xsave.stride(0), model.embed_layers.err.data_ptr(), L.current_stream_ptr())
+            L.check(rc, "rtf_embed_dot_peer_fwd")
         ctx.model, ctx.ids = model, ids
         ctx.save_for_backward(dense, xsave)
         return out
@@ -605,6 +619,8 @@ class _PeerDotFn(torch.autograd.Function):
             model.rank * B, L.current_stream_ptr())
         L.check(rc, "rtf_embed_dot_peer_bwd")
         model._pending = True
+        if model.async_update:      # barrier + K2 on the exchange stream, behind the bottom MLP's
+            model._launch_update()  # backward; the trainer's finish_backward() only waits
         return None, None, gdense, None
 
 
@@ -673,6 +689,9 @@ class PeerShardedDLRM(Layer):
         self._pending = False
         self._prepared = None
         self._out_inflight = False      # peers may still be pulling the previous forward's rows
+        self.async_update = False       # set by ShardedDLRMTrainer: K2 behind the MLP backward
+        self._xstream = None            # exchange stream: K1 + barrier + row pull, barrier + K2
+        self._upd_ev = None
         # replicated block: the shards of rep_fields are contiguous at the end of the table buffer
         self._Ts, self._Tr = len(lay.shard_fields[self.rank]), len(lay.rep_fields)
         self._rep_rows = [rows[t] for t in lay.rep_fields]
@@ -714,6 +733,7 @@ class PeerShardedDLRM(Layer):
                                                     self._out_hdl.buffer_ptrs, D, self.rank)
             self._d_peer_optr = torch.tensor(optr, dtype=torch.int64, device=dev)
             self._d_peer_ostr = torch.tensor(ostr, dtype=torch.int64, device=dev)
+            self._xsave = torch.empty((B_local, lay.n_tables * D), dtype=torch.float32, device=dev)
         self._grad_B = B_local
 
     def call(self, inputs, **kwargs):
@@ -737,28 +757,76 @@ class PeerShardedDLRM(Layer):
                 self._prepared_rep = self.embed_layers.prepare_backward(
                     ids_rep, [self._Ts + j for j in range(self._Tr)])
         if owner:
+            # K1 over my shards for the GLOBAL batch -> barrier -> pull of my samples' rows, all on
+            # the exchange stream: it overlaps the bottom MLP below (tensor-core GEMMs)
+            cur = torch.cuda.current_stream()
+            if self._xstream is None:
+                self._xstream = torch.cuda.Stream()
+            xs = self._xstream
+            self.finish_backward()          # a pending row update must land before K1 reads the tables
+            xs.wait_stream(cur)
             Tme = self._Ts + self._Tr
             Bg = B_local * self.world
-            if self._out_inflight:   # no grad barrier since the last forward (eval, or a forward
-                self._out_hdl.barrier(channel=1)     # never followed by finish_backward): peers may
-                #                                      still be reading the previous batch's rows
-            out_view = self._out_buf[: Bg * Tme * self.D].view(Bg, Tme * self.D)
-            W = list(self.embed_layers.weights)
-            with torch.no_grad():
-                if self._Ts:    # foreign lookups of row-wise tables (-1) are skipped silently
-                    embed_fwd(W[: self._Ts], loc, "BF", None, err=None, out=out_view, skip_invalid=True)
-                if self._Tr:    # replicated tables: local gather for my own samples
-                    mine = out_view[self.rank * B_local: (self.rank + 1) * B_local, self._Ts * self.D:]
-                    embed_fwd(W[self._Ts:], ids_rep, "BF", None, err=self.embed_layers.err, out=mine)
-        dense_fea = self.bot_dnn(dense_inputs)
-        # owner: every holder's rows are in place; direct: every rank's row updates of the previous
-        # step are complete before anyone pulls from the tables
-        (self._out_hdl if owner else self._tab_hdl).barrier(channel=0)
+            with torch.cuda.stream(xs):
+                if self._out_inflight:   # no grad barrier since the last forward (eval, or a forward
+                    self._out_hdl.barrier(channel=1)     # never followed by finish_backward): peers may
+                    #                                      still be reading the previous batch's rows
+                out_view = self._out_buf[: Bg * Tme * self.D].view(Bg, Tme * self.D)
+                W = list(self.embed_layers.weights)
+                with torch.no_grad():
+                    if self._Ts:    # foreign lookups of row-wise tables (-1) are skipped silently
+                        embed_fwd(W[: self._Ts], loc, "BF", None, err=None, out=out_view, skip_invalid=True)
+                    if self._Tr:    # replicated tables: local gather for my own samples
+                        mine = out_view[self.rank * B_local: (self.rank + 1) * B_local, self._Ts * self.D:]
+                        embed_fwd(W[self._Ts:], ids_rep, "BF", None, err=self.embed_layers.err, out=mine)
+                self._out_hdl.barrier(channel=0)     # every holder's rows are in place
+                F = self.layout.n_tables
+                rc = L.lib().rtf_peer_pull_rows(
+                    self._d_peer_optr.data_ptr(), self._d_peer_ostr.data_ptr(), self.rank * B_local,
+                    self.world, self.layout.rw_mask, self._rows_arr, F, self.D, sparse_inputs.data_ptr(),
+                    int(sparse_inputs.dtype == torch.int64), B_local, sparse_inputs.stride(0),
+                    sparse_inputs.stride(1), self._xsave.data_ptr(), self._xsave.stride(0),
+                    self.embed_layers.err.data_ptr(), xs.cuda_stream)
+                L.check(rc, "rtf_peer_pull_rows")
+                pulled = torch.cuda.Event()
+                pulled.record(xs)
+            for t in (loc, ids_rep, sparse_inputs):
+                if t is not None:
+                    t.record_stream(xs)
+            dense_fea = self.bot_dnn(dense_inputs)
+            cur.wait_event(pulled)
+        else:
+            self.finish_backward()
+            dense_fea = self.bot_dnn(dense_inputs)
+            # every rank's row updates of the previous step are complete before anyone pulls
+            self._tab_hdl.barrier(channel=0)
         x = _PeerDotFn.apply(self, sparse_inputs, dense_fea, self.pad_to)
         self._out_inflight = owner
         return torch.sigmoid(self.final_dense(self.top_dnn(x)))
 
+    def _launch_update(self):
+        """barrier + K2 (+ replicated rows) on the exchange stream, ordered after the K4 backward
+        that was just enqueued on the current stream."""
+        cur = torch.cuda.current_stream()
+        if self._xstream is None:
+            self._xstream = torch.cuda.Stream()
+        xs = self._xstream
+        xs.wait_stream(cur)
+        with torch.cuda.stream(xs):
+            self._finish_backward_impl()
+            self._upd_ev = torch.cuda.Event()
+            self._upd_ev.record(xs)
+
     def finish_backward(self):
+        """Complete the embedding update of the last backward on the current stream: either wait
+        for the exchange stream (async_update) or run barrier + K2 here."""
+        if self._upd_ev is not None:
+            torch.cuda.current_stream().wait_event(self._upd_ev)
+            self._upd_ev = None
+        if self._pending:
+            self._finish_backward_impl()
+
+    def _finish_backward_impl(self):
         """Replicated tables: per-rank segment sums (K2, reduce only) -> dense all-reduce (async).
         Sharded tables: all peers' dX rows have landed in this rank's gradient buffer -> K2
         (+ sparse optimizer) on the local shards.  Then the replicated rows' update."""
