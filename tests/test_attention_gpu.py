@@ -200,7 +200,8 @@ def test_autoint_fused_layer_fwd_bwd_vs_fp64(rtf, B, F, dm, H, hs, use_res, act)
         want = want.detach().numpy()
         _close(got.detach().cpu().numpy(), want, rtol=1e-5, atol=1e-5 * max(np.abs(want).max(), 1e-30))
     close(out, ref)
-    close(xt.grad, x64.grad)
+    w = x64.grad.numpy()            # 128-term fp32 dots of O(1) values: 2e-5 of the largest entry
+    _close(xt.grad.cpu().numpy(), w, rtol=1e-5, atol=2e-5 * np.abs(w).max())
     for d, W in zip(dens, Ws):      # a fp32 reduction over B*F terms: tolerance scaled accordingly
         w = W.grad.numpy()
         _close(d.kernel.grad.cpu().numpy(), w, rtol=1e-5, atol=5e-5 * np.abs(w).max())

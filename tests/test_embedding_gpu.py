@@ -254,3 +254,61 @@ def test_autograd_lookup_fused_and_sparse(rtf):
     (out * out).sum().backward()
     for w2, r in zip(ts2.weights, ref):
         torch.testing.assert_close(w2.detach(), r.detach() - 0.5 * r.grad, rtol=1e-5, atol=1e-6)
+
+
+@pytest.mark.parametrize("kind", ["adam", "adagrad", "sgd"])
+def test_rows_apply_dense_matches_row_update_restatement(rtf, kind):
+    """rtf_rows_apply_dense (replicated small tables, multi-GPU) == the torch restatement of K2's
+    row update that the CPU tests check against the oracle, bit for bit; untouched rows keep
+    their values and state."""
+    import ctypes as C
+    from recommend_tf2_b200 import _lib as L
+    from recommend_tf2_b200.sharded import apply_touched_rows
+    torch.manual_seed(0)
+    R, D = 1000, 128
+    opt = rtf.SparseOptimizer(kind, lr=1e-2, l2=1e-4)
+    W = torch.randn(R, D, device="cuda") * 0.05
+    m = torch.rand(R, D, device="cuda") * 0.01
+    v = torch.rand(R, D, device="cuda") * 0.001
+    G = torch.zeros(R + 1, D + 1, device="cuda")
+    G[:R, :D] = torch.randn(R, D, device="cuda")
+    G[:R, D] = (torch.rand(R, device="cuda") < 0.4).float() * 3.0
+    st = opt.struct_for_step(5)
+    want = [t.clone() for t in (W, m, v)]
+    apply_touched_rows(opt, st.lr, want[0], want[1] if opt.n_states >= 1 else None,
+                       want[2] if opt.n_states >= 2 else None, G)
+    g, touched = G[:R, :D].contiguous(), G[:R, D].contiguous()
+    rc = L.lib().rtf_rows_apply_dense(W.data_ptr(), m.data_ptr() if opt.n_states >= 1 else None,
+                                      v.data_ptr() if opt.n_states >= 2 else None, g.data_ptr(),
+                                      touched.data_ptr(), R, D, C.byref(st), L.current_stream_ptr())
+    assert rc == 0
+    assert torch.equal(W, want[0])
+    if opt.n_states >= 1:
+        assert torch.equal(m, want[1])
+    if opt.n_states >= 2:
+        assert torch.equal(v, want[2])
+
+
+def test_dense_adam_matches_keras_formula(rtf):
+    """core.DenseAdam (rtf_dense_adam over the flat buffer) == Keras Adam (App. A12) in fp64."""
+    from recommend_tf2_b200.core import DenseAdam
+    torch.manual_seed(1)
+    ps = [torch.nn.Parameter(torch.randn(n, device="cuda")) for n in (33, 1024, 7)]
+    ref = [p.detach().double().cpu() for p in ps]
+    mm = [torch.zeros_like(r) for r in ref]
+    vv = [torch.zeros_like(r) for r in ref]
+    opt = DenseAdam(ps, lr=1e-2)
+    for t in range(1, 6):
+        opt.zero_grad()
+        gs = [torch.randn_like(p) for p in ps]
+        for p, g in zip(ps, gs):
+            p.grad.add_(g)
+        opt.step()
+        lr_t = 1e-2 * (1 - 0.999 ** t) ** 0.5 / (1 - 0.9 ** t)
+        for r, m_, v_, g in zip(ref, mm, vv, gs):
+            g = g.double().cpu()
+            m_.mul_(0.9).add_(0.1 * g)
+            v_.mul_(0.999).add_(0.001 * g * g)
+            r.sub_(lr_t * m_ / (v_.sqrt() + 1e-7))
+    for p, r in zip(ps, ref):
+        torch.testing.assert_close(p.detach().double().cpu(), r, rtol=1e-5, atol=1e-6)
