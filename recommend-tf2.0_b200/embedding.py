@@ -280,7 +280,10 @@ class EmbeddingTables(torch.nn.Module):
             st = opt.struct_for_step(max(opt.step, 1))
         rows = [int(w.shape[0]) for w in self.weights]
         dims = [int(w.shape[1]) for w in self.weights]
-        torch.cuda.current_stream().wait_event(h["ev"])
+        cur = torch.cuda.current_stream()
+        cur.wait_event(h["ev"])
+        h["ws"].record_stream(cur)      # the work list may be consumed on a stream other than the
+        #                                 one it was allocated / prepared on (exchange stream)
         rc = lib.rtf_embed_bwd_apply(_ptr_array([w.data for w in self.weights]), _ptr_array(self.state1),
                                      _ptr_array(self.state2), L.host_array(C.c_int64, rows),
                                      L.host_array(C.c_int32, dims), len(rows),
