@@ -64,6 +64,9 @@ def parse_args():
                     help="peer exchange: rows gathered by their holders (K1) and pulled by sample, or "
                          "pulled straight from the remote table shards")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-pipeline", action="store_true",
+                    help="multi-GPU: do not hand the next batch's ids to the step (no pipelining of the "
+                         "embedding exchange behind the previous step)")
     ap.add_argument("--no-parity-check", action="store_true",
                     help="skip the untimed sharded-vs-single-GPU self-check run before a multi-GPU measurement")
     ap.add_argument("--no-kernel-timing", action="store_true")
@@ -174,7 +177,9 @@ def bench_config(args, world):
             f"tables sharded over {world} GPUs ({args.exchange} row exchange"
             + (f"/{args.peer_gather} gather, row-wise >= {args.row_wise_min_rows} rows, "
                f"replicated <= {args.replicate_max_rows} rows" if args.exchange == "peer" else "")
-            + ") + dp MLP"}
+            + ") + dp MLP"
+            + ("" if (world == 1 or args.no_pipeline) else
+               "; exchange of batch n+1 (ids, holder gather, NVLink pull) pipelined behind step n")}
 
 
 def reference_config(args):
@@ -419,14 +424,18 @@ def run_b200(args):
 
     # ---- device-resident timing (value)
     sampler = ClockSampler(local_rank) if rank == 0 else None
+    # multi-GPU: the NEXT batch's sparse ids are handed to the step (a prefetching feeder has
+    # them): its embedding exchange is pipelined behind the current step (sharded.py prefetch)
+    pipelined = world > 1 and not args.no_pipeline
+    nxt = (lambda i: {"next_sparse": dev[i + 1][1]} if pipelined and i + 1 < len(dev) else {})
     for i in range(W):
-        trainer.step(*dev[i])
+        trainer.step(*dev[i], **nxt(i))
     barrier()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     t_start = time.time()
     e0.record()
     for i in range(W, W + K):
-        trainer.step(*dev[i])
+        trainer.step(*dev[i], **nxt(i))
     e1.record()
     barrier()
     t_end = time.time()
@@ -441,8 +450,13 @@ def run_b200(args):
     f0, f1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     f0.record()
     # the public input path: pinned host batches -> DeviceFeeder (copy stream, one step ahead)
-    for i, (d, s, y) in enumerate(pkg.DeviceFeeder(host[W:W + K])):
-        loss = trainer.step(d, s, y)
+    feeder = pkg.DeviceFeeder(host[W:W + K])
+    for i, (d, s, y) in enumerate(feeder):
+        if pipelined:
+            nb = feeder.peek_next()
+            loss = trainer.step(d, s, y, next_sparse=None if nb is None else nb[1])
+        else:
+            loss = trainer.step(d, s, y)
         loss_host[i].copy_(loss, non_blocking=True)
     f1.record()
     barrier()

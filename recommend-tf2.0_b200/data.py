@@ -112,7 +112,7 @@ class DeviceFeeder:
         return True
 
     def __iter__(self) -> Iterator[Tuple[torch.Tensor, ...]]:
-        queue = []
+        queue = self._queue = []
         for slot in self.slots:
             if not self._fill(slot):
                 break
@@ -127,3 +127,15 @@ class DeviceFeeder:
             slot["free"].record(torch.cuda.current_stream(self.device))
             if self._fill(slot):
                 queue.append(slot)
+
+    def peek_next(self) -> Optional[Tuple[torch.Tensor, ...]]:
+        """Inside the loop body: the device tensors of the NEXT batch (already on their way over
+        the copy stream), or None after the last one.  The current stream is made to wait for
+        that copy, so the tensors may be read by work enqueued from now on — e.g. to start the
+        next batch's embedding exchange behind the current step (ShardedDLRMTrainer.step)."""
+        queue = getattr(self, "_queue", None)
+        if not queue:
+            return None
+        slot = queue[0]
+        torch.cuda.current_stream(self.device).wait_event(slot["ready"])
+        return slot["dev"]

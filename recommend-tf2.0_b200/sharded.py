@@ -393,7 +393,10 @@ class ShardedDLRMTrainer:
         if hasattr(m, "async_update"):
             m.async_update = True       # step() always ends with finish_backward()
 
-    def step(self, dense, sparse, labels) -> torch.Tensor:
+    def step(self, dense, sparse, labels, next_sparse=None) -> torch.Tensor:
+        """next_sparse: the NEXT batch's sparse ids, if the caller already has them (a prefetching
+        feeder does): the embedding exchange of batch n+1 is then pipelined behind step n
+        (PeerShardedDLRM.prefetch) and leaves the critical path."""
         m = self.model
         if self.dense_opt is None:
             self._setup(dense)
@@ -406,11 +409,15 @@ class ShardedDLRMTrainer:
         # asynchronous so that it overlaps the reverse exchange barrier + K2 on the embedding
         # shards (finish_backward)
         work = dist.all_reduce(self.dense_opt.flat_grad, async_op=True)
-        if not getattr(m, "async_update", False):
+        pipelined = next_sparse is not None and hasattr(m, "prefetch") and m.async_update
+        if pipelined:
+            m.prefetch(next_sparse)
+        elif not getattr(m, "async_update", False):
             m.finish_backward()
         work.wait()
         self.dense_opt.step()
-        m.finish_backward()             # async: the row update ran behind the MLP backward / Adam
+        if not pipelined:
+            m.finish_backward()         # async: the row update ran behind the MLP backward / Adam
         return loss.detach()
 
 
@@ -703,6 +710,7 @@ class PeerShardedDLRM(Layer):
         self.async_update = False       # set by ShardedDLRMTrainer: K2 behind the MLP backward
         self._xstream = None            # exchange stream: K1 + barrier + row pull, barrier + K2
         self._loc_cache = {}
+        self._prefetched = None         # exchange of a batch announced with prefetch()
         self._upd_ev = None
         # replicated block: the shards of rep_fields are contiguous at the end of the table buffer
         self._Ts, self._Tr = len(lay.shard_fields[self.rank]), len(lay.rep_fields)
@@ -748,34 +756,39 @@ class PeerShardedDLRM(Layer):
             self._xsave = torch.empty((B_local, lay.n_tables * D), dtype=torch.float32, device=dev)
         self._grad_B = B_local
 
-    def call(self, inputs, **kwargs):
-        dense_inputs, sparse_inputs = inputs
+    def _exchange(self, sparse_inputs, train: bool):
+        """Everything of a batch that depends on its ids only: the id all-gather, K2's keys / sort /
+        segments (side stream) and — owner gather — K1 over my shards for the GLOBAL batch, the
+        barrier and the NVLink pull of my samples' rows into the local staging buffer, all on the
+        exchange stream.  Returns what the interaction / the backward need."""
         B_local = sparse_inputs.shape[0]
         self._ensure_grad_buffer(B_local)
-        train = torch.is_grad_enabled() and self.embed_layers.optimizer is not None
         owner = self.gather == "owner"
+        ex = {"key": (sparse_inputs.data_ptr(), tuple(sparse_inputs.shape), sparse_inputs._version),
+              "prepared": None, "prepared_rep": None, "ids_rep": None, "pulled": None, "train": train}
+        loc = None
         if train or owner:
             # the holders need the ids of the global batch for their shards (104 B/sample): K1 in
             # owner mode, and K2 — whose keys, sort and segments start now on a side stream
             ids_global = exchange_ids(sparse_inputs, self.world)
             loc = local_shard_ids(ids_global, self.layout, self.rank, self._loc_cache)
             if train and loc.shape[1]:
-                self._prepared = self.embed_layers.prepare_backward(loc, list(range(loc.shape[1])))
+                ex["prepared"] = self.embed_layers.prepare_backward(loc, list(range(loc.shape[1])))
         ids_rep = None
         if self._Tr:
             ids_rep = sparse_inputs.index_select(1, self._rep_idx).contiguous()   # my samples only
-            self._saved_rep_ids = ids_rep
+            ex["ids_rep"] = ids_rep
             if train:   # keys / sort / segments of the replicated lookups: side stream as well
-                self._prepared_rep = self.embed_layers.prepare_backward(
+                ex["prepared_rep"] = self.embed_layers.prepare_backward(
                     ids_rep, [self._Ts + j for j in range(self._Tr)])
         if owner:
             # K1 over my shards for the GLOBAL batch -> barrier -> pull of my samples' rows, all on
-            # the exchange stream: it overlaps the bottom MLP below (tensor-core GEMMs)
+            # the exchange stream: it overlaps the bottom MLP (tensor-core GEMMs) or, when the batch
+            # was announced with prefetch(), the tail of the previous step
             cur = torch.cuda.current_stream()
             if self._xstream is None:
                 self._xstream = torch.cuda.Stream()
             xs = self._xstream
-            self.finish_backward()          # a pending row update must land before K1 reads the tables
             xs.wait_stream(cur)
             Tme = self._Ts + self._Tr
             Bg = B_local * self.world
@@ -800,20 +813,48 @@ class PeerShardedDLRM(Layer):
                     sparse_inputs.stride(1), self._xsave.data_ptr(), self._xsave.stride(0),
                     self.embed_layers.err.data_ptr(), xs.cuda_stream)
                 L.check(rc, "rtf_peer_pull_rows")
-                pulled = torch.cuda.Event()
-                pulled.record(xs)
+                ex["pulled"] = torch.cuda.Event()
+                ex["pulled"].record(xs)
             for t in (loc, ids_rep, sparse_inputs):
                 if t is not None:
                     t.record_stream(xs)
-            dense_fea = self.bot_dnn(dense_inputs)
-            cur.wait_event(pulled)
+            self._out_inflight = True
+        return ex
+
+    def prefetch(self, sparse_next) -> None:
+        """Announce the NEXT batch's sparse ids (call it after backward()): its exchange is
+        enqueued right behind this step's row update on the exchange stream, so the id exchange,
+        holder-side K1, the barrier and the NVLink pull all hide behind the tail of this step and
+        the head of the next one.  Same arithmetic, same order of table reads and writes as the
+        un-pipelined step (K2 of step n precedes K1 of step n+1 on the one exchange stream)."""
+        if self.gather != "owner" or sparse_next is None:
+            return
+        if self._pending and self._upd_ev is None:      # no async update was launched: do it now
+            self._finish_backward_impl()
+        train = self.embed_layers.optimizer is not None
+        self._prefetched = self._exchange(sparse_next, train)
+
+    def call(self, inputs, **kwargs):
+        dense_inputs, sparse_inputs = inputs
+        train = torch.is_grad_enabled() and self.embed_layers.optimizer is not None
+        owner = self.gather == "owner"
+        ex, pf = None, self._prefetched
+        self._prefetched = None
+        if pf is not None and pf["key"] == (sparse_inputs.data_ptr(), tuple(sparse_inputs.shape),
+                                            sparse_inputs._version) and (pf["train"] or not train):
+            ex = pf                     # announced by prefetch(): the rows are (being) pulled already
         else:
-            self.finish_backward()
-            dense_fea = self.bot_dnn(dense_inputs)
+            self.finish_backward()      # a pending row update must land before K1 reads the tables
+            ex = self._exchange(sparse_inputs, train)
+        self._prepared, self._prepared_rep = ex["prepared"], ex["prepared_rep"]
+        self._saved_rep_ids = ex["ids_rep"]
+        dense_fea = self.bot_dnn(dense_inputs)
+        if owner:
+            torch.cuda.current_stream().wait_event(ex["pulled"])
+        else:
             # every rank's row updates of the previous step are complete before anyone pulls
             self._tab_hdl.barrier(channel=0)
         x = _PeerDotFn.apply(self, sparse_inputs, dense_fea, self.pad_to)
-        self._out_inflight = owner
         return torch.sigmoid(self.final_dense(self.top_dnn(x)))
 
     def _launch_update(self):
@@ -924,7 +965,8 @@ def parity_self_check(exchange: str = "peer", gather: str = "owner", replicate_m
     two forwards: the peer-mapped row buffer must not be overwritten under a reader).  Returns
     {"world", "modes", "max_rel_err", "max_rel_err_state", "ok", ...}; never raises on a
     mismatch — the caller decides.  MirroredStrategy semantics (src/ctr/fm/train.py:43-50): the
-    sharded run must be indistinguishable from one replica seeing the global batch."""
+    sharded run must be indistinguishable from one replica seeing the global batch.  The training
+    steps hand the next batch's ids to the trainer, so the pipelined exchange is what is checked."""
     from .dlrm import DLRM, DLRMTrainer
     rank, world = dist.get_rank(), dist.get_world_size()
     rows = [37 + 11 * t for t in range(F)]
@@ -975,14 +1017,18 @@ def parity_self_check(exchange: str = "peer", gather: str = "owner", replicate_m
             pd.copy_(ps)
         rel(sharded([dense[sl], sparse[sl]]), single([dense, sparse])[sl], "fwd")
         rel(sharded([dense[sl], sparse[sl]]), single([dense, sparse])[sl], "fwd")   # 2 forwards, no bwd
-    for _ in range(steps):
+    my_sparse = sparse[sl]
+    for it in range(steps):
         l1 = t1.step(dense, sparse, y)
-        l2 = t2.step(dense[sl], sparse[sl], y[sl])
+        # the next batch is announced: its exchange is pipelined behind this step (prefetch hit on
+        # the next training step; after an eval forward consumed it, the inline path runs instead)
+        l2 = t2.step(dense[sl], my_sparse, y[sl], next_sparse=my_sparse)
         lsum = l2.clone()
         dist.all_reduce(lsum)
         rel(lsum / world, l1, "fwd")
-        with torch.no_grad():   # eval forward between two training steps
-            rel(sharded([dense[sl], sparse[sl]]), single([dense, sparse])[sl], "fwd")
+        if it >= 1:
+            with torch.no_grad():   # eval forward between two training steps
+                rel(sharded([dense[sl], my_sparse]), single([dense, sparse])[sl], "fwd")
     for j, t in enumerate(mine):
         rel(sharded.embed_layers.weights[j], shard_of(single.embed_layers.weights[t], t), "state")
         rel(sharded.embed_layers.state1[j], shard_of(single.embed_layers.state1[t], t), "state")
