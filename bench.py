@@ -437,6 +437,7 @@ def run_b200(args):
     for i in range(W, W + K):
         trainer.step(*dev[i], **nxt(i))
     e1.record()
+    host_ms = (time.time() - t_start) * 1e3 / K     # host enqueue time (the CPU runs ahead of the GPU)
     barrier()
     t_end = time.time()
     ms_total = e0.elapsed_time(e1)
@@ -526,6 +527,7 @@ def run_b200(args):
                 "e2e": {"value": B * world * K / (ms_e2e * 1e-3), "unit": "samples/s",
                         "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 4,
                         "ms_per_step": ms_e2e / K},
+                "host_enqueue_ms_per_step": round(host_ms, 3),
                 "gpu_launches": per_step * K, "roofline": roof, "kernels": kernels,
                 "cpu_baseline": cpu, "final_loss": float(loss_host[-1])}
         if parity is not None:

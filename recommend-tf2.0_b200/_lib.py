@@ -160,8 +160,13 @@ def require_cuda(t, what: str):
 
 
 def current_stream_ptr() -> int:
+    """Raw cudaStream_t of torch's current stream (the C call, not the Stream object: this runs
+    ~60 times per training step and the host must stay ahead of the GPU)."""
     import torch
-    return torch.cuda.current_stream().cuda_stream
+    try:
+        return torch._C._cuda_getCurrentRawStream(torch._C._cuda_getDevice())
+    except AttributeError:      # private API moved: the public, slower route
+        return torch.cuda.current_stream().cuda_stream
 
 
 def host_array(ctype, values):

@@ -202,14 +202,33 @@ def dense_gemm(kind: str, a: torch.Tensor, b: torch.Tensor, bias=None, relu: boo
         batch, K = splits, K // splits
         sa, sb, sd = K * lda, K * ldb, M * N
     out = torch.empty((batch, M, N) if batch > 1 else (M, N), dtype=torch.float32, device=a.device)
-    nb = C.c_size_t(0)
-    L.check(wsq(M, N, K, batch, C.byref(nb)), f"rtf_dense_gemm_{kind}_workspace")
-    ws = torch.empty(max(nb.value, 16), dtype=torch.uint8, device=a.device)
+    key = (kind, M, N, K, batch)
+    if key not in _GEMM_WS_BYTES:
+        nb = C.c_size_t(0)
+        L.check(wsq(M, N, K, batch, C.byref(nb)), f"rtf_dense_gemm_{kind}_workspace")
+        _GEMM_WS_BYTES[key] = max(nb.value, 16)
+    ws = _scratch(_GEMM_WS_BYTES[key], a.device)
     rc = fn(a.data_ptr(), lda, sa, b.data_ptr(), ldb, sb, None if bias is None else bias.data_ptr(),
             int(relu), out.data_ptr(), N, sd, M, N, K, batch, ws.data_ptr(), ws.numel(),
             L.current_stream_ptr())
     L.check(rc, f"rtf_dense_gemm_{kind}")
     return out.sum(0) if batch > 1 else out
+
+
+_GEMM_WS_BYTES: dict = {}
+_SCRATCH: dict = {}
+
+
+def _scratch(nbytes: int, device) -> torch.Tensor:
+    """A reusable kernel-scratch buffer per (device, stream): launches on one stream are ordered,
+    so consecutive GEMMs / reductions may share it (saves an allocator round trip per launch —
+    ~60 per training step, and the host has to stay ahead of the GPU)."""
+    key = (device.index, torch._C._cuda_getCurrentRawStream(device.index if device.index is not None
+                                                            else torch._C._cuda_getDevice()))
+    buf = _SCRATCH.get(key)
+    if buf is None or buf.numel() < nbytes:
+        buf = _SCRATCH[key] = torch.empty(max(nbytes, 1 << 20), dtype=torch.uint8, device=device)
+    return buf
 
 
 def _wgrad_splits(B: int, kin: int, n: int, clusters: int = 74) -> int:
@@ -250,9 +269,12 @@ def _relu_bwd_bias_grad(gy: torch.Tensor, y):
         import ctypes as C
         from . import _lib as L
         gy = gy.contiguous()
-        nb = C.c_size_t(0)
-        L.check(L.lib().rtf_relu_bwd_colsum_workspace(B, N, C.byref(nb)), "rtf_relu_bwd_colsum_workspace")
-        ws = torch.empty(nb.value, dtype=torch.uint8, device=gy.device)
+        key = ("relu_bwd", B, N)
+        if key not in _GEMM_WS_BYTES:
+            nb = C.c_size_t(0)
+            L.check(L.lib().rtf_relu_bwd_colsum_workspace(B, N, C.byref(nb)), "rtf_relu_bwd_colsum_workspace")
+            _GEMM_WS_BYTES[key] = max(nb.value, 16)
+        ws = _scratch(_GEMM_WS_BYTES[key], gy.device)
         g = torch.empty_like(gy) if y is not None else gy
         db = torch.empty(N, dtype=torch.float32, device=gy.device)
         L.check(L.lib().rtf_relu_bwd_colsum(gy.data_ptr(), None if y is None else y.data_ptr(), B, N,

@@ -220,6 +220,18 @@ class EmbeddingTables(torch.nn.Module):
             self.set_optimizer(optimizer)
         return self
 
+    def wlist(self):
+        """The tables as a plain Python list (ParameterList indexing costs ~2 us per access and
+        the step touches the list hundreds of times)."""
+        wl = self.__dict__.get("_wl")
+        if wl is None or len(wl) != len(self.weights):
+            wl = self.__dict__["_wl"] = list(self.weights)
+            self.__dict__["_rows"] = [int(w.shape[0]) for w in wl]
+            self.__dict__["_dims"] = [int(w.shape[1]) for w in wl]
+            self.__dict__["_rows_arr"] = L.host_array(C.c_int64, self._rows)
+            self.__dict__["_dims_arr"] = L.host_array(C.c_int32, self._dims)
+        return wl
+
     def set_optimizer(self, optimizer: Optional[SparseOptimizer]):
         self.optimizer = optimizer
         n = 0 if optimizer is None else optimizer.n_states
@@ -234,9 +246,10 @@ class EmbeddingTables(torch.nn.Module):
     def lookup(self, ids: torch.Tensor, field_table: Optional[Sequence[int]] = None,
                layout: str = "BF", pool: Optional[str] = None) -> torch.Tensor:
         self.wait_pending()
+        wl = self.wlist()
         if field_table is None:
-            field_table = list(range(len(self.weights)))
-        return _LookupFn.apply(self, ids, tuple(field_table), layout, pool, *self.weights)
+            field_table = list(range(len(wl)))
+        return _LookupFn.apply(self, ids, tuple(field_table), layout, pool, *wl)
 
     # ---- K2 split: id-only half on a side stream, gradient half on the critical path
     def prepare_backward(self, ids, field_table, layout="BF"):
@@ -244,12 +257,15 @@ class EmbeddingTables(torch.nn.Module):
         only) so they overlap the dense forward/backward; returns a handle for apply_prepared."""
         lib = L.lib()
         B, F, Lq, sb, sf, sl = ids_strides(ids, layout)
-        rows = [int(w.shape[0]) for w in self.weights]
-        dims = [int(w.shape[1]) for w in self.weights]
+        self.wlist()
+        rows, dims = self._rows, self._dims
         n = B * F * Lq
-        nbytes = C.c_size_t(0)
-        L.check(lib.rtf_embed_bwd_workspace(n, max(dims), C.byref(nbytes)), "rtf_embed_bwd_workspace")
-        ws = torch.empty(max(nbytes.value, 16), dtype=torch.uint8, device=ids.device)
+        wsz = self.__dict__.setdefault("_ws_bytes", {})
+        if (n, max(dims)) not in wsz:
+            nbytes = C.c_size_t(0)
+            L.check(lib.rtf_embed_bwd_workspace(n, max(dims), C.byref(nbytes)), "rtf_embed_bwd_workspace")
+            wsz[(n, max(dims))] = max(nbytes.value, 16)
+        ws = torch.empty(wsz[(n, max(dims))], dtype=torch.uint8, device=ids.device)
         self.wait_pending()
         cur = torch.cuda.current_stream()
         if getattr(self, "_side", None) is None:
@@ -257,7 +273,7 @@ class EmbeddingTables(torch.nn.Module):
         side = self._side
         side.wait_stream(cur)
         with torch.cuda.stream(side):
-            rc = lib.rtf_embed_bwd_prepare(L.host_array(C.c_int64, rows), L.host_array(C.c_int32, dims),
+            rc = lib.rtf_embed_bwd_prepare(self._rows_arr, self._dims_arr,
                                            len(rows), L.host_array(C.c_int32, list(field_table)), F,
                                            ids.data_ptr(), int(ids.dtype == torch.int64), B, Lq, sb, sf,
                                            sl, None, None, ws.data_ptr(), ws.numel(), side.cuda_stream)
@@ -278,15 +294,15 @@ class EmbeddingTables(torch.nn.Module):
             st = L.rtf_opt(L.OPT_NONE, 0.0, 0.0, 0.0, 0.0, 0.0)
         else:
             st = opt.struct_for_step(max(opt.step, 1))
-        rows = [int(w.shape[0]) for w in self.weights]
-        dims = [int(w.shape[1]) for w in self.weights]
+        wl = self.wlist()
+        rows = self._rows
         cur = torch.cuda.current_stream()
         cur.wait_event(h["ev"])
         h["ws"].record_stream(cur)      # the work list may be consumed on a stream other than the
         #                                 one it was allocated / prepared on (exchange stream)
-        rc = lib.rtf_embed_bwd_apply(_ptr_array([w.data for w in self.weights]), _ptr_array(self.state1),
-                                     _ptr_array(self.state2), L.host_array(C.c_int64, rows),
-                                     L.host_array(C.c_int32, dims), len(rows),
+        rc = lib.rtf_embed_bwd_apply(_ptr_array(wl), _ptr_array(self.state1),
+                                     _ptr_array(self.state2), self._rows_arr,
+                                     self._dims_arr, len(rows),
                                      L.host_array(C.c_int32, list(h["field_table"])), h["F"], h["B"],
                                      h["L"], _POOL[pool], grad.data_ptr(), grad.stride(0),
                                      C.byref(st),

@@ -85,7 +85,8 @@ class _EmbedDotFn(torch.autograd.Function):
         gout = gout.contiguous()
         B, F = ids.shape
         D = dense.shape[1]
-        tables = [tset.weights[t] for t in field_table]
+        wl = tset.wlist()
+        tables = [wl[t] for t in field_table]
         rows = L.host_array(C.c_int64, [int(t.shape[0]) for t in tables])
         gdense = torch.empty_like(dense)
         gemb = torch.empty((B, F * D), dtype=torch.float32, device=ids.device)
@@ -104,7 +105,7 @@ class _EmbedDotFn(torch.autograd.Function):
                 tset.apply_prepared_async(ctx.prepared, gemb)
             else:
                 tset.apply_prepared(ctx.prepared, gemb)
-            return (None, None, None, None, gdense) + (None,) * len(tset.weights)
+            return (None, None, None, None, gdense) + (None,) * len(wl)
         wgrads = tset.grads_from_lookup_grad(ids, field_table, gemb, "BF", None)
         return (None, None, None, None, gdense) + wgrads
 
@@ -115,7 +116,8 @@ def embed_dot(tset: EmbeddingTables, ids: torch.Tensor, dense: torch.Tensor,
     gathered rows in HBM.  ids (B, F) int32/int64, dense (B, D)."""
     if ids.dtype not in (torch.int32, torch.int64):
         raise TypeError("ids must be int32 or int64")
+    wl = tset.wlist()
     if field_table is None:
-        field_table = tuple(range(len(tset.weights)))
+        field_table = tuple(range(len(wl)))
     tset.wait_pending()
-    return _EmbedDotFn.apply(tset, ids, tuple(field_table), pad_to, dense, *tset.weights)
+    return _EmbedDotFn.apply(tset, ids, tuple(field_table), pad_to, dense, *wl)
