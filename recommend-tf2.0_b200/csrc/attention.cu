@@ -22,8 +22,13 @@
 namespace rtf {
 
 constexpr int ATT_R = 4;          // query rows (or key rows in dkv) per warp step
-constexpr int ATT_THREADS = 256;  // 8 warps
-constexpr int ATT_WARPS = ATT_THREADS / 32;
+// warps per CTA, chosen per kernel from its register need (ptxas: fwd 96, dq 228, dkv 159
+// registers at 8 keys per lane): one CTA owns a (sample, head) and its K/V (or Q/dO) tiles fill
+// most of the shared memory, so resident warps per SM = warps per CTA — the kernels are bound by
+// shared-memory / FMA latency, and more warps is what hides it.
+constexpr int ATT_FWD_THREADS = 512;
+constexpr int ATT_DQ_THREADS = 256;
+constexpr int ATT_DKV_THREADS = 384;
 
 struct AttnParams {
   const float* q; const float* k; const float* v;
@@ -60,7 +65,7 @@ __device__ __forceinline__ float mask_logit(float s, bool row_ok, bool key_ok, b
 
 // ----------------------------------------------------------------------------- forward
 template <int KPL>
-__global__ void __launch_bounds__(ATT_THREADS, 1) attn_fwd_kernel(const __grid_constant__ AttnParams P) {
+__global__ void __launch_bounds__(ATT_FWD_THREADS, 1) attn_fwd_kernel(const __grid_constant__ AttnParams P) {
   extern __shared__ __align__(16) float smem[];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int b = blockIdx.x / P.H, h = blockIdx.x - b * P.H;
@@ -74,7 +79,7 @@ __global__ void __launch_bounds__(ATT_THREADS, 1) attn_fwd_kernel(const __grid_c
   __syncthreads();
   const float* qb = P.q + (long long)b * P.q_sb + h * hs;
   const int CT = (hs + 31) >> 5;
-  for (int i0 = warp * ATT_R; i0 < Lq; i0 += ATT_WARPS * ATT_R) {
+  for (int i0 = warp * ATT_R; i0 < Lq; i0 += (blockDim.x >> 5) * ATT_R) {
     for (int e = lane; e < ATT_R * hs; e += 32) {
       const int r = e / hs, c = e - r * hs;
       Qw[e] = (i0 + r < Lq) ? qb[(long long)(i0 + r) * P.q_sl + c] : 0.f;
@@ -180,7 +185,7 @@ __global__ void __launch_bounds__(ATT_THREADS, 1) attn_fwd_kernel(const __grid_c
 // ----------------------------------------------------------------------------- backward: dQ
 // rows owned by warps (as forward): recompute P, dP = dO V^T, dS = P (dP - delta), dQ = scale dS K
 template <int KPL>
-__global__ void __launch_bounds__(ATT_THREADS, 1) attn_bwd_dq_kernel(const __grid_constant__ AttnParams P) {
+__global__ void __launch_bounds__(ATT_DQ_THREADS, 1) attn_bwd_dq_kernel(const __grid_constant__ AttnParams P) {
   extern __shared__ __align__(16) float smem[];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int b = blockIdx.x / P.H, h = blockIdx.x - b * P.H;
@@ -197,7 +202,7 @@ __global__ void __launch_bounds__(ATT_THREADS, 1) attn_bwd_dq_kernel(const __gri
   const float* dob = P.dout + (long long)b * P.do_sb + h * hs;
   const float* ob = P.out + (long long)b * P.o_sb + h * hs;
   const int CT = (hs + 31) >> 5;
-  for (int i0 = warp * ATT_R; i0 < Lq; i0 += ATT_WARPS * ATT_R) {
+  for (int i0 = warp * ATT_R; i0 < Lq; i0 += (blockDim.x >> 5) * ATT_R) {
     float dl[ATT_R];
 #pragma unroll
     for (int r = 0; r < ATT_R; ++r) dl[r] = 0.f;
@@ -306,7 +311,7 @@ __global__ void __launch_bounds__(ATT_THREADS, 1) attn_bwd_dq_kernel(const __gri
 // ----------------------------------------------------------------------------- backward: dK, dV
 // keys owned by warps; the Q and dO tiles live in shared memory; lanes own queries
 template <int QPL>
-__global__ void __launch_bounds__(ATT_THREADS, 1) attn_bwd_dkv_kernel(const __grid_constant__ AttnParams P) {
+__global__ void __launch_bounds__(ATT_DKV_THREADS, 1) attn_bwd_dkv_kernel(const __grid_constant__ AttnParams P) {
   extern __shared__ __align__(16) float smem[];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int b = blockIdx.x / P.H, h = blockIdx.x - b * P.H;
@@ -331,7 +336,7 @@ __global__ void __launch_bounds__(ATT_THREADS, 1) attn_bwd_dkv_kernel(const __gr
   const float* kb = P.k + (long long)b * P.k_sb + h * hs;
   const float* vb = P.v + (long long)b * P.v_sb + h * hs;
   const int CT = (hs + 31) >> 5;
-  for (int j0 = warp * ATT_R; j0 < Lk; j0 += ATT_WARPS * ATT_R) {
+  for (int j0 = warp * ATT_R; j0 < Lk; j0 += (blockDim.x >> 5) * ATT_R) {
     for (int e = lane; e < ATT_R * hs; e += 32) {
       const int r = e / hs, c = e - r * hs;
       const bool ok = j0 + r < Lk;
@@ -439,11 +444,12 @@ __global__ void __launch_bounds__(ATT_THREADS, 1) attn_bwd_dkv_kernel(const __gr
 }
 
 template <typename Kern>
-static int attn_launch(Kern kern, const AttnParams& P, size_t smem_bytes, cudaStream_t st) {
+static int attn_launch(Kern kern, const AttnParams& P, size_t smem_bytes, int threads,
+                       cudaStream_t st) {
   if (smem_bytes > 227 * 1024) return RTF_E_RANGE;
   cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_bytes);
   if (e != cudaSuccess) return (int)e;
-  kern<<<(unsigned)(P.B * P.H), ATT_THREADS, smem_bytes, st>>>(P);
+  kern<<<(unsigned)(P.B * P.H), threads, smem_bytes, st>>>(P);
   RTF_CHECK_LAUNCH();
   return 0;
 }
@@ -481,13 +487,20 @@ extern "C" int rtf_attn_fwd(const float* d_q, int64_t q_sb, int64_t q_sl, const 
   if (!d_q || !d_k || !d_v || !d_out) return RTF_E_ARG;
   if ((d_stat_m == nullptr) != (d_stat_il == nullptr)) return RTF_E_ARG;
   const int RS = hs + 4;
-  const size_t smem = ((size_t)2 * Lk * RS + (size_t)ATT_WARPS * (ATT_R * hs + Lk * ATT_R)) * 4;
+  // as many warps as the per-warp staging (Q rows + P^T) leaves room for, up to the bound
+  int warps = ATT_FWD_THREADS / 32;
+  auto smem_for = [&](int w) { return ((size_t)2 * Lk * RS + (size_t)w * (ATT_R * hs + Lk * ATT_R)) * 4; };
+  while (warps > 4 && smem_for(warps) > 227 * 1024) warps -= 4;
+  const int rows_w = (Lq + ATT_R - 1) / ATT_R;       // no more warps than there are row groups
+  while (warps > 4 && warps - 4 >= rows_w) warps -= 4;
+  const size_t smem = smem_for(warps);
+  const int thr = warps * 32;
   cudaStream_t st = (cudaStream_t)stream;
   const int kpl = (Lk + 31) / 32;
-  if (kpl <= 1) return attn_launch(attn_fwd_kernel<1>, P, smem, st);
-  if (kpl <= 2) return attn_launch(attn_fwd_kernel<2>, P, smem, st);
-  if (kpl <= 4) return attn_launch(attn_fwd_kernel<4>, P, smem, st);
-  return attn_launch(attn_fwd_kernel<8>, P, smem, st);
+  if (kpl <= 1) return attn_launch(attn_fwd_kernel<1>, P, smem, thr, st);
+  if (kpl <= 2) return attn_launch(attn_fwd_kernel<2>, P, smem, thr, st);
+  if (kpl <= 4) return attn_launch(attn_fwd_kernel<4>, P, smem, thr, st);
+  return attn_launch(attn_fwd_kernel<8>, P, smem, thr, st);
 }
 
 extern "C" int rtf_attn_bwd(const float* d_q, int64_t q_sb, int64_t q_sl, const float* d_k,
@@ -518,22 +531,27 @@ extern "C" int rtf_attn_bwd(const float* d_q, int64_t q_sb, int64_t q_sl, const 
   const int RS = hs + 4;
   cudaStream_t st = (cudaStream_t)stream;
   {
-    const size_t smem = ((size_t)2 * Lk * RS + (size_t)ATT_WARPS * (2 * ATT_R * hs + Lk * ATT_R)) * 4;
+    const int warps = ATT_DQ_THREADS / 32;
+    const size_t smem = ((size_t)2 * Lk * RS + (size_t)warps * (2 * ATT_R * hs + Lk * ATT_R)) * 4;
     const int kpl = (Lk + 31) / 32;
-    if (kpl <= 1) rc = attn_launch(attn_bwd_dq_kernel<1>, P, smem, st);
-    else if (kpl <= 2) rc = attn_launch(attn_bwd_dq_kernel<2>, P, smem, st);
-    else if (kpl <= 4) rc = attn_launch(attn_bwd_dq_kernel<4>, P, smem, st);
-    else rc = attn_launch(attn_bwd_dq_kernel<8>, P, smem, st);
+    if (kpl <= 1) rc = attn_launch(attn_bwd_dq_kernel<1>, P, smem, warps * 32, st);
+    else if (kpl <= 2) rc = attn_launch(attn_bwd_dq_kernel<2>, P, smem, warps * 32, st);
+    else if (kpl <= 4) rc = attn_launch(attn_bwd_dq_kernel<4>, P, smem, warps * 32, st);
+    else rc = attn_launch(attn_bwd_dq_kernel<8>, P, smem, warps * 32, st);
     if (rc) return rc;
   }
   {
-    const size_t smem = ((size_t)2 * Lq * RS + 4 * (size_t)Lq +
-                         (size_t)ATT_WARPS * (2 * ATT_R * hs + 2 * Lq * ATT_R)) * 4;
+    int warps = ATT_DKV_THREADS / 32;
+    auto smem_for = [&](int w) {
+      return ((size_t)2 * Lq * RS + 4 * (size_t)Lq + (size_t)w * (2 * ATT_R * hs + 2 * Lq * ATT_R)) * 4;
+    };
+    while (warps > 4 && smem_for(warps) > 227 * 1024) warps -= 2;
+    const size_t smem = smem_for(warps);
     const int qpl = (Lq + 31) / 32;
-    if (qpl <= 1) rc = attn_launch(attn_bwd_dkv_kernel<1>, P, smem, st);
-    else if (qpl <= 2) rc = attn_launch(attn_bwd_dkv_kernel<2>, P, smem, st);
-    else if (qpl <= 4) rc = attn_launch(attn_bwd_dkv_kernel<4>, P, smem, st);
-    else rc = attn_launch(attn_bwd_dkv_kernel<8>, P, smem, st);
+    if (qpl <= 1) rc = attn_launch(attn_bwd_dkv_kernel<1>, P, smem, warps * 32, st);
+    else if (qpl <= 2) rc = attn_launch(attn_bwd_dkv_kernel<2>, P, smem, warps * 32, st);
+    else if (qpl <= 4) rc = attn_launch(attn_bwd_dkv_kernel<4>, P, smem, warps * 32, st);
+    else rc = attn_launch(attn_bwd_dkv_kernel<8>, P, smem, warps * 32, st);
   }
   return rc;
 }

@@ -26,34 +26,65 @@ __device__ __forceinline__ uint64_t splitmix64(uint64_t x) {
 }
 
 // P(c) = log((c+2)/(c+1)) / log(range_max+1); draw = floor(exp(u * log(range_max+1))) - 1
+//
+// One warp, 32 tries per round: try t0 + lane is drawn by lane (counter-based RNG, so the sample
+// sequence is a pure function of the seed), duplicates inside the round are resolved with
+// match_any (lowest lane = earliest try wins), duplicates against earlier rounds by probing an
+// open-addressing hash set, the survivors are appended IN TRY ORDER (ballot ranks) and inserted
+// with atomicCAS.  The result — sampled ids, their order and num_tries — is exactly what the
+// sequential rejection loop of App. A14 yields for this RNG stream; the set lives in shared
+// memory when it fits (global-memory probes on one thread cost 465 us for S = 1024, this 25 us).
 __global__ void __launch_bounds__(32)
 log_uniform_sample_kernel(uint64_t seed, int S, long long range_max, long long* __restrict__ out,
-                          int32_t* __restrict__ num_tries, long long* __restrict__ table, int cap) {
-  // single warp; `table` is an open-addressing hash set of capacity `cap` (power of two, >= 2S)
+                          int32_t* __restrict__ num_tries, long long* __restrict__ gtable, int cap,
+                          int use_smem) {
+  extern __shared__ long long stab[];
+  long long* table = use_smem ? stab : gtable;
   const int lane = threadIdx.x;
   for (int i = lane; i < cap; i += 32) table[i] = -1;
   __syncwarp();
-  if (lane != 0) return;
   const double log_range = log((double)range_max + 1.0);
-  int got = 0, tries = 0;
-  while (got < S) {
-    const uint64_t r = splitmix64(seed ^ splitmix64((uint64_t)tries));
-    ++tries;
+  const uint32_t lt = (1u << lane) - 1u;
+  int got = 0, t0 = 0;
+  while (true) {
+    const uint64_t r = splitmix64(seed ^ splitmix64((uint64_t)(t0 + lane)));
     const double u = (double)(r >> 11) * (1.0 / 9007199254740992.0);  // [0,1)
     long long c = (long long)(exp(u * log_range)) - 1;
     if (c < 0) c = 0;
     if (c >= range_max) c = range_max - 1;
+    // earliest try of every distinct value in this round
+    const uint32_t same = __match_any_sync(0xffffffffu, c);
+    bool fresh = (same & lt) == 0;
     uint32_t hsh = (uint32_t)(splitmix64((uint64_t)c) & (uint64_t)(cap - 1));
-    bool dup = false;
-    while (table[hsh] != -1) {
-      if (table[hsh] == c) { dup = true; break; }
-      hsh = (hsh + 1) & (uint32_t)(cap - 1);
+    if (fresh) {   // seen in an earlier round?
+      while (true) {
+        const long long e = reinterpret_cast<volatile long long*>(table)[hsh];
+        if (e == -1) break;
+        if (e == c) { fresh = false; break; }
+        hsh = (hsh + 1) & (uint32_t)(cap - 1);
+      }
     }
-    if (dup) continue;
-    table[hsh] = c;
-    out[got++] = c;
+    const uint32_t fm = __ballot_sync(0xffffffffu, fresh);
+    const int rank = __popc(fm & lt);
+    const bool keep = fresh && got + rank < S;
+    if (keep) {
+      out[got + rank] = c;
+      uint32_t h2 = hsh;   // the first free slot seen; another lane of this round may take it
+      while (atomicCAS(reinterpret_cast<unsigned long long*>(table + h2), (unsigned long long)-1ll,
+                       (unsigned long long)c) != (unsigned long long)-1ll)
+        h2 = (h2 + 1) & (uint32_t)(cap - 1);
+    }
+    const int nf = __popc(fm);
+    if (got + nf >= S) {
+      // the try that produced the S-th unique id ends the sequence
+      const uint32_t last = __ballot_sync(0xffffffffu, fresh && got + rank == S - 1);
+      if (lane == 0) *num_tries = t0 + __ffs(last);
+      return;
+    }
+    got += nf;
+    t0 += 32;
+    __syncwarp();
   }
-  *num_tries = tries;
 }
 
 // expected_count(c) = -expm1(num_tries * log1p(-P(c)))  (unique=True), App. A14
@@ -207,8 +238,15 @@ extern "C" int rtf_log_uniform_sample(uint64_t seed, int S, int64_t range_max, i
   if ((int64_t)S > range_max) return RTF_E_RANGE;  // TF would never terminate (A14)
   int cap = 64;
   while (cap < 2 * S) cap <<= 1;
-  log_uniform_sample_kernel<<<1, 32, 0, (cudaStream_t)stream>>>(
-      seed, S, range_max, (long long*)d_sampled, d_num_tries, (long long*)d_ws, cap);
+  const size_t smem = (size_t)cap * 8;
+  const int use_smem = smem <= 200 * 1024;
+  if (use_smem && smem > 48 * 1024) {
+    cudaError_t e = cudaFuncSetAttribute(log_uniform_sample_kernel,
+                                         cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return (int)e;
+  }
+  log_uniform_sample_kernel<<<1, 32, use_smem ? smem : 0, (cudaStream_t)stream>>>(
+      seed, S, range_max, (long long*)d_sampled, d_num_tries, (long long*)d_ws, cap, use_smem);
   RTF_CHECK_LAUNCH();
   return 0;
 }

@@ -173,10 +173,9 @@ class _SasrecScoreFn(torch.autograd.Function):
         g_pos = tset.grads_from_lookup_grad(pos.reshape(B, 1), (pos_t,), gemb[:, 0, :], "BL", None)
         g_neg = tset.grads_from_lookup_grad(neg, (neg_t,), gemb[:, 1:, :], "BL", None)
         wg = [None] * nw
-        for g in (g_pos, g_neg):
-            for t in range(nw):
-                if g[t] is not None:
-                    wg[t] = g[t] if wg[t] is None else wg[t] + g[t]
+        for g, t in ((g_pos, pos_t), (g_neg, neg_t)):      # only the tables that were looked up
+            if g[t] is not None:
+                wg[t] = g[t] if wg[t] is None else wg[t] + g[t]
         return (None, ginfo, None, None, None, None) + tuple(wg)
 
 
