@@ -204,6 +204,7 @@ dot_fwd_kernel(const __grid_constant__ DotParams P, int warp_floats) {
   }
 }
 
+#ifdef RTF_DOT_EXPERIMENTS  // measured-slower variants: records in profiles/, not in the default build
 // Forward, variant 2 (D % 8 == 0; opt-in with RTF_DOT_FWD_V2=1, parity tests pass with it).
 // Measured on B200, DLRM configuration: 0.418 ms vs 0.368 ms for variant 1 — the 25 % fewer
 // shared-memory wavefronts do not pay for the 64-accumulator tile (128 registers + spill, one
@@ -331,6 +332,8 @@ dot_fwd_kernel_v2(const __grid_constant__ DotParams P, int warp_floats, int cta_
   }
 }
 
+#endif  // RTF_DOT_EXPERIMENTS
+
 // backward: dX[i] = sum_j S[i][j] X[j],  S symmetric from dZ, plus the passthrough on row 0
 template <typename IdT>
 __global__ void __launch_bounds__(512, 1)
@@ -448,6 +451,7 @@ dot_bwd_kernel(const __grid_constant__ DotParams P, int warp_floats) {
   }
 }
 
+#ifdef RTF_DOT_EXPERIMENTS
 // ------------------------------------------------------------------------------------------
 // Tensor-core variants for F1 <= 32, D % 8 == 0 (the DLRM shape: 27 x 128).
 //
@@ -681,6 +685,8 @@ static bool dot_use_mma(int F1, int D) {
   return use_mma && F1 <= 32 && D % 8 == 0;
 }
 
+#endif  // RTF_DOT_EXPERIMENTS
+
 static int dot_check_common(long long B, int F1, int D) {
   if (B < 0 || F1 < 2 || D <= 0) return RTF_E_ARG;
   if (F1 > RTF_MAX_FIELDS || D % 4 || D > 1024) return RTF_E_RANGE;
@@ -705,6 +711,7 @@ static int dot_launch(Kern kern, const DotParams& P, int warp_floats, int cta_fl
   return 0;
 }
 
+#ifdef RTF_DOT_EXPERIMENTS
 template <typename Kern>
 static int dot_launch_v2(Kern kern, const DotParams& P, int warp_floats, int cta_floats,
                          cudaStream_t st) {
@@ -729,9 +736,12 @@ static bool dot_use_fwd_v2(int D) {
   return on && D % 8 == 0;
 }
 
+#endif  // RTF_DOT_EXPERIMENTS
+
 static int dot_fwd_impl(DotParams& P, int ids_i64, cudaStream_t st) {
   const int F1p = (P.F1 + 3) & ~3, RS = dot_row_stride(P.D);
   const int npairs = P.F1 * (P.F1 - 1) / 2;
+#ifdef RTF_DOT_EXPERIMENTS
   if (dot_use_fwd_v2(P.D)) {
     const int wf = F1p * RS + ((npairs + 3) & ~3) + 4;
     const int cf = 64;  // tile table: <= 72 tiles x 2 bytes, padded to 256 B
@@ -743,6 +753,7 @@ static int dot_fwd_impl(DotParams& P, int ids_i64, cudaStream_t st) {
     return ids_i64 ? dot_launch(dot_fwd_mma_kernel<int64_t>, P, wf, 0, st)
                    : dot_launch(dot_fwd_mma_kernel<int32_t>, P, wf, 0, st);
   }
+#endif
   const int warp_floats = F1p * RS + ((npairs + 3) & ~3) + 4;  // + mbarrier (8 B, 16-B slot)
   return ids_i64 ? dot_launch(dot_fwd_kernel<int64_t>, P, warp_floats, 0, st)
                  : dot_launch(dot_fwd_kernel<int32_t>, P, warp_floats, 0, st);
@@ -750,12 +761,14 @@ static int dot_fwd_impl(DotParams& P, int ids_i64, cudaStream_t st) {
 static int dot_bwd_impl(DotParams& P, int ids_i64, cudaStream_t st) {
   const int F1p = (P.F1 + 7) & ~7, RS = dot_row_stride(P.D);
   const int npairs = P.F1 * (P.F1 - 1) / 2;
+#ifdef RTF_DOT_EXPERIMENTS
   if (dot_use_mma(P.F1, P.D) && !P.peer_gptr) {
     const int wf = 32 * dot_row_stride_bwd(P.D) + 32 * 36 + 4;
     const int cf = ((npairs + 1) / 2 + 3) & ~3;
     return ids_i64 ? dot_launch(dot_bwd_mma_kernel<int64_t>, P, wf, cf, st)
                    : dot_launch(dot_bwd_mma_kernel<int32_t>, P, wf, cf, st);
   }
+#endif
   const int warp_floats = P.F1 * RS + F1p * F1p + 4 + 128;  // + mbarrier slot + 64 ids
   const int cta_floats = ((npairs + 1) / 2 + 3) & ~3;
   return ids_i64 ? dot_launch(dot_bwd_kernel<int64_t>, P, warp_floats, cta_floats, st)

@@ -225,27 +225,29 @@ extern "C" int rtf_topk_ip(const float* d_users, int64_t u_ld, int64_t B, const 
   topk_init<<<(unsigned)((nc + 255) / 256), 256, 0, st>>>(cval, cidx, nc);
   RTF_CHECK_LAUNCH();
   const unsigned rb = (unsigned)((B + TK_WARPS - 1) / TK_WARPS);
-  for (int64_t i0 = 0; i0 < N; i0 += T) {
-    // the GEMM's N must be a multiple of 4: a ragged last tile starts a little earlier and the
-    // merge skips the columns (`first`) that the previous tile already covered
-    int64_t n = N - i0 < T ? N - i0 : T;
-    int64_t start = i0;
-    int first = 0;
-    if (n % 4) {
-      const int64_t n4 = (n + 3) / 4 * 4;
-      if (N >= n4) {
-        start = N - n4;
-        first = (int)(i0 - start);
-        n = n4;
-      } else {
-        return RTF_E_RANGE;  // fewer than 4 items in total and N % 4 != 0
-      }
-    }
-    rc = rtf_dense_gemm_nt(d_users, u_ld, 0, d_items + start * i_ld, i_ld, 0, nullptr, 0, scores, T,
-                           0, (int)B, (int)n, D, 1, gws, tk_align(g), stream);
-    if (rc) return rc;
+  // one GEMM + merge over items [start, start + n), of which the columns >= first are new
+  auto run_tile = [&](int64_t start, int64_t n, int first) -> int {
+    int r = rtf_dense_gemm_nt(d_users, u_ld, 0, d_items + start * i_ld, i_ld, 0, nullptr, 0, scores, T,
+                              0, (int)B, (int)n, D, 1, gws, tk_align(g), stream);
+    if (r) return r;
     topk_merge_tile<<<rb, TK_WARPS * 32, 0, st>>>(scores, T, first, (int)n, start, cval, cidx, B);
     RTF_CHECK_LAUNCH();
+    return 0;
+  };
+  for (int64_t i0 = 0; i0 < N; i0 += T) {
+    // the GEMM's N must be a multiple of 4: a ragged last tile is cut into its multiple-of-4 part
+    // and the LAST FOUR items of the table, whose columns already covered are skipped (`first`)
+    const int64_t n = N - i0 < T ? N - i0 : T;
+    const int64_t n_main = n - n % 4;
+    if (n_main > 0) {
+      rc = run_tile(i0, n_main, 0);
+      if (rc) return rc;
+    }
+    if (n % 4) {
+      if (N < 4) return RTF_E_RANGE;
+      rc = run_tile(N - 4, 4, (int)(4 - n % 4));
+      if (rc) return rc;
+    }
   }
   topk_rescore<<<rb, TK_WARPS * 32, 0, st>>>(d_users, u_ld, d_items, i_ld, N, D, cval, cidx, k,
                                              (long long*)d_out_idx, d_out_score, d_flag, B);

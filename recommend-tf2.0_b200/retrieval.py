@@ -61,4 +61,5 @@ class IndexFlatIP:
         q = torch.as_tensor(q, dtype=torch.float32)
         if not q.is_cuda:
             q = q.cuda()
-        return topk_ip(q, self._items, k)
+        # faiss leaves the order of exact ties unspecified; here: lower index first, no exception
+        return topk_ip(q, self._items, k, check=False)
