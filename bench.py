@@ -286,18 +286,75 @@ def time_kernels(pkg, model, dev_batches, peaks_gbs):
         keys = ids + (torch.arange(F, device="cuda").view(1, F) << 32)
         uniq.append(int(torch.unique(keys).numel()))
 
-    def k2(i):
-        pkg.embed_bwd([w.data for w in ts.weights], list(range(F)), dev_batches[i][1], gemb, "BF", None,
+    # K2 as the training step runs it: the id-only half (keys, sort, segments, work items) on the
+    # side stream behind the dense MLP, the gradient half = ONE launch (seg_apply) timed here
+    prepared = {}
+
+    def k2_prepare(i):
+        prepared[i] = ts.prepare_backward(dev_batches[i][1], list(range(F)))
+        torch.cuda.current_stream().wait_event(prepared[i]["ev"])
+
+    for i in range(n):
+        k2_prepare(i)
+    ms = timed(lambda i: ts.apply_prepared(prepared[i], gemb), n)
+    by = B * F * D * 4 + statistics.mean(uniq) * 6 * D * 4
+    res["seg_apply(K2: segment reduce + sparse Adam)"] = (ms, by)
+
+    def k2(i):      # the whole pipeline on one stream (keys + sort + segments + work items + apply)
+        pkg.embed_bwd(ts.wlist(), list(range(F)), dev_batches[i][1], gemb, "BF", None,
                       opt=opt, state1=ts.state1, state2=ts.state2)
     ms = timed(k2, n)
     by = B * F * (4 + D * 4) + statistics.mean(uniq) * 6 * D * 4
-    res["embed_bwd(K2 sort+segment+adam)"] = (ms, by)
+    res["embed_bwd(K2 pipeline: keys+sort+segments+apply, 24 launches)"] = (ms, by)
     out = {}
     for k, (ms, by) in res.items():
         gbs = by / (ms * 1e-3) / 1e9
         out[k] = {"ms": round(ms, 4), "algorithmic_bytes": int(by), "gbs": round(gbs, 1),
                   "frac_hbm": round(gbs / peaks_gbs, 4)}
     return out
+
+
+def time_dense_gemm(pkg, peaks):
+    """The dense-MLP GEMM (60 % of the step) against ITS roofline: fp32-equivalent
+    TFLOP/s of the 65 536 x 1024 x 1024 layer (forward / dgrad / wgrad) over the measured
+    sustained bf16 tensor peak divided by 6 — the kernel issues 6 bf16 products per fp32 product."""
+    import torch
+    from recommend_tf2_b200 import core
+    M, N, K = 65536, 1024, 1024
+    x = torch.randn(M, K, device="cuda")
+    w = torch.randn(K, N, device="cuda") * 0.03
+    b = torch.zeros(N, device="cuda")
+    g = torch.randn(M, N, device="cuda")
+    peak = peaks.get("bf16_tflops_sustained", peaks.get("bf16_tflops", 1590.0)) / 6.0
+    out = {}
+
+    def timed(fn, n=6):
+        for _ in range(3):
+            fn()
+        torch.cuda.synchronize()
+        evs = []
+        for _ in range(n):
+            a_, b_ = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            a_.record()
+            fn()
+            b_.record()
+            evs.append((a_, b_))
+        torch.cuda.synchronize()
+        return statistics.median(p.elapsed_time(q) for p, q in evs)
+
+    for name, fn in (("fwd (nn, bias+ReLU)", lambda: core.dense_gemm("nn", x, w, b, True)),
+                     ("dgrad (nt)", lambda: core.dense_gemm("nt", g, w)),
+                     ("wgrad (tn, split-K)", lambda: core._wgrad(x, g))):
+        ms = timed(fn)
+        tf = 2.0 * M * N * K / (ms * 1e-3) / 1e12
+        out[name] = {"ms": round(ms, 4), "tflops_fp32_equiv": round(tf, 1), "frac": round(tf / peak, 4)}
+    worst = min(out.values(), key=lambda v: v["frac"])
+    return {"kernel": "rtf_dense_gemm_* (tcgen05 2-SM, fp32 split into 3 bf16 terms, 6 products; CUTLASS "
+                      "collective instantiated in csrc/dense_gemm.cuh)",
+            "bound": "tensor", "unit": "TFLOP/s", "peak": round(peak, 1),
+            "peak_source": "MEASURED_PEAKS.json bf16_tflops_sustained / 6 (fp32-equivalent ceiling)",
+            "shape": [M, N, K], "achieved": worst["tflops_fp32_equiv"], "frac": worst["frac"],
+            "by_layout": out}
 
 
 def count_own_launches(trainer, batch):
@@ -473,27 +530,41 @@ def run_b200(args):
     if rank == 0:
         kernels = None
         roof = None
+        roof_compute = None
         if not args.no_kernel_timing and world == 1:
             kernels = time_kernels(pkg, model, dev[W:W + min(K, 8)], peaks["hbm_gbs"])
-            # DRAM traffic per launch from the committed `ncu --set full` capture of the same kernels on
-            # the same workload (profiles/r1_ncu_traffic.json); null when a kernel was not captured
-            traffic = {}
-            tpath = os.path.join(ROOT, "profiles", "r1_ncu_traffic.json")
+            # DRAM traffic per launch: from the committed `ncu --set full` capture of the same
+            # kernels on the same workload (profiles/r2_ncu_traffic.json) — NOT measured in this
+            # run; the entry names its source so a stale capture is visible
+            traffic, tsrc = {}, None
+            tpath = os.path.join(ROOT, "profiles", "r2_ncu_traffic.json")
             if os.path.exists(tpath) and B == 65536 and args.ids == "uniform":
                 with open(tpath) as f:
-                    traffic = {k: int(v["traffic_bytes"]) for k, v in json.load(f)["kernels"].items()}
+                    tj = json.load(f)
+                traffic = {k: int(v["traffic_bytes"]) for k, v in tj["kernels"].items()}
+                tsrc = tj.get("source")
             for k, v in kernels.items():
                 v["traffic_bytes_ncu"] = traffic.get(k)
                 # DRAM-side rate: tables smaller than L2 (11 of the 26) are served from L2, so the
                 # algorithmic rate of a gather can exceed the HBM peak while the DRAM rate does not
                 v["dram_gbs_ncu_traffic"] = (round(traffic[k] / (v["ms"] * 1e-3) / 1e9, 1)
                                              if k in traffic else None)
-            top = max(kernels.items(), key=lambda kv: kv[1]["ms"])
+            # the dominant SINGLE kernel of the embedding path inside the training step (K1 alone
+            # and the multi-launch K2 pipeline are reported under "kernels" but are not step kernels)
+            in_step = {k: v for k, v in kernels.items() if not k.startswith(("embed_fwd_vec", "embed_bwd("))}
+            top = max(in_step.items(), key=lambda kv: kv[1]["ms"])
             roof = {"kernel": top[0], "bound": "hbm", "achieved": top[1]["gbs"],
                     "peak": peaks["hbm_gbs"], "unit": "GB/s", "frac": top[1]["frac_hbm"],
-                    "traffic": traffic.get(top[0]), "peak_source": peak_src,
+                    "traffic": traffic.get(top[0]), "traffic_source": tsrc, "peak_source": peak_src,
                     "algorithmic_bytes_per_launch": top[1]["algorithmic_bytes"],
                     "ms_per_launch": top[1]["ms"]}
+            path_ms = sum(v["ms"] for v in in_step.values())
+            path_by = sum(v["algorithmic_bytes"] for v in in_step.values())
+            roof["embedding_path_in_step"] = {
+                "kernels": list(in_step), "ms": round(path_ms, 4), "algorithmic_bytes": int(path_by),
+                "gbs": round(path_by / (path_ms * 1e-3) / 1e9, 1),
+                "frac_hbm": round(path_by / (path_ms * 1e-3) / 1e9 / peaks["hbm_gbs"], 4)}
+            roof_compute = time_dense_gemm(pkg, peaks)
         cpu = None
         if not args.no_cpu_baseline and world == 1:     # reported on rank 0 at N=1 only
             cpu = cpu_reference_run(args, steps=3, warmup=1)
@@ -528,7 +599,8 @@ def run_b200(args):
                         "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 4,
                         "ms_per_step": ms_e2e / K},
                 "host_enqueue_ms_per_step": round(host_ms, 3),
-                "gpu_launches": per_step * K, "roofline": roof, "kernels": kernels,
+                "gpu_launches": per_step * K, "roofline": roof, "roofline_compute": roof_compute,
+                "kernels": kernels,
                 "cpu_baseline": cpu, "final_loss": float(loss_host[-1])}
         if parity is not None:
             line["parity_check"] = parity

@@ -55,7 +55,7 @@ def main():
                                               gout.data_ptr(), cols, gdense.data_ptr(), D,
                                               gemb.data_ptr(), F * D, L.current_stream_ptr()), "bwd")
         if "k2" in which:
-            ts.apply_sparse_grad(ids, list(range(F)), gemb)
+            ts.apply_sparse_grad(ids, list(range(F)), gemb)   # keys, sort, segments, work items, seg_apply
     torch.cuda.synchronize()
     print("prof_kernels done")
 
