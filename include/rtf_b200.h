@@ -297,6 +297,29 @@ int rtf_sampled_softmax_bwd(const float* d_x, int64_t x_sb, const float* d_W, co
                             const float* d_gloss, float* d_gx, int64_t gx_sb, float* d_G,
                             void* d_ws, void* stream);
 
+/* K8, GEMM form for large S (same semantics as rtf_sampled_softmax_{fwd,bwd}): the (B, S) sampled
+ * logits x . Ws^T come from the tensor-core GEMM (rtf_dense_gemm_nt) and these entry points do
+ * the rest.  _gather: Ws (S, D) = W[sampled], cs[j] = bias[s_j] - log(samp_exp[j]).
+ * _logits_fwd: true logit, accidental-hit removal, log-sum-exp -> loss, lse.
+ * _logits_bwd: g0 (B) and G1 (B, S; row stride g1_ld) = d loss / d [true | sampled] logits;
+ *   the caller then forms gx = G1 . Ws (rtf_dense_gemm_nn) and the weight-row gradients
+ *   [g0 * x | G1^T . x] (rtf_dense_gemm_tn).  _true_gx: gx[b] += g0[b] * W[label[b]].          */
+int rtf_ssm_gather(const float* d_W, const float* d_bias, const int64_t* d_sampled,
+                   const float* d_samp_exp, int64_t N, int S, int D, float* d_Ws, float* d_cs,
+                   int32_t* d_err, void* stream);
+int rtf_ssm_logits_fwd(const float* d_logits, int64_t ld, const float* d_x, int64_t x_sb,
+                       const float* d_W, const float* d_bias, const int64_t* d_labels,
+                       const int64_t* d_sampled, const float* d_true_exp, const float* d_cs,
+                       int64_t B, int64_t N, int S, int D, int remove_hits, float* d_loss,
+                       float* d_lse, int32_t* d_err, void* stream);
+int rtf_ssm_logits_bwd(const float* d_logits, int64_t ld, const float* d_x, int64_t x_sb,
+                       const float* d_W, const float* d_bias, const int64_t* d_labels,
+                       const int64_t* d_sampled, const float* d_true_exp, const float* d_cs,
+                       int64_t B, int64_t N, int S, int D, int remove_hits, const float* d_lse,
+                       const float* d_gloss, float* d_g0, float* d_G1, int64_t g1_ld, void* stream);
+int rtf_ssm_true_gx(const float* d_W, const int64_t* d_labels, const float* d_g0, int64_t B,
+                    int64_t N, int D, float* d_gx, int64_t gx_sb, void* stream);
+
 /* ---- dense-layer backward epilogue (MLP either side of the path) ------------
  * replaces: ReluGrad + BiasAddGrad after the Dense layers of ctr.layers.modules.DNN
  *           (src/ctr/layers/modules.py:129-135) — two passes over the (B,N) gradient become one.

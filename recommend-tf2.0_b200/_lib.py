@@ -75,6 +75,12 @@ SIGNATURES = {
     "rtf_topk_ip": [_p, _i64, _i64, _p, _i64, _i64, _int, _int, _p, _p, _p, _p, C.c_size_t, _p],
     "rtf_peer_pull_rows": [_p, _p, _i64, _int, C.c_uint64, _p, _int, _int, _p, _int, _i64, _i64, _i64, _p,
                            _i64, _p, _p],
+    "rtf_ssm_gather": [_p, _p, _p, _p, _i64, _int, _int, _p, _p, _p, _p],
+    "rtf_ssm_logits_fwd": [_p, _i64, _p, _i64, _p, _p, _p, _p, _p, _p, _i64, _i64, _int, _int, _int, _p, _p,
+                           _p, _p],
+    "rtf_ssm_logits_bwd": [_p, _i64, _p, _i64, _p, _p, _p, _p, _p, _p, _i64, _i64, _int, _int, _int, _p, _p,
+                           _p, _p, _i64, _p],
+    "rtf_ssm_true_gx": [_p, _p, _p, _i64, _i64, _int, _p, _i64, _p],
     "rtf_dense_adam": [_p, _p, _p, _p, _i64, C.POINTER(rtf_opt), _p],
     "rtf_rows_apply_dense": [_p, _p, _p, _p, _p, _i64, _int, C.POINTER(rtf_opt), _p],
     "rtf_dense_gemm_nn_workspace": [_int, _int, _int, _int, C.POINTER(C.c_size_t)],

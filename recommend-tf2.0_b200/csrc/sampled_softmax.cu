@@ -207,6 +207,98 @@ __global__ void __launch_bounds__(256) ssm_kernel(const __grid_constant__ SsmPar
   }
 }
 
+// ---- GEMM form (large S): the (B, S) sampled logits come from the tensor-core GEMM
+// x (B,D) . Ws^T (S,D) (rtf_dense_gemm_nt, fp32-accurate) instead of every sample's warp
+// re-streaming all S sampled rows from L2 (S = 1024, D = 64: 1.07 GB of L2 reads per launch,
+// 0.35 ms = 2 % of the FMA peak); these kernels are the per-sample epilogues around it.
+struct SsmLogitParams {
+  const float* logits; long long ld;   // (B, S) raw x . w_s
+  const float* x; long long x_sb;
+  const float* W; const float* bias;
+  const long long* labels; const long long* sampled;
+  const float* true_exp; const float* cs;   // cs[j] = bias[s_j] - log(samp_exp[j]) (ssm_gather)
+  long long B, N;
+  int S, D, remove_hits;
+  float* loss; float* lse;
+  const float* gloss;
+  float* g0; float* G1; long long g1_ld;    // bwd: dL/dlogit true (B) and sampled (B, S)
+  float* gx; long long gx_sb;               // bwd: gx += g0 * W[label]
+  int32_t* err;
+};
+
+__device__ __forceinline__ float ssm_true_logit(const SsmLogitParams& P, long long b, int lane,
+                                                bool& lab_ok) {
+  const long long label = P.labels[b];
+  lab_ok = label >= 0 && label < P.N;
+  float t0 = 0.f;
+  if (lab_ok)
+    for (int c = lane; c < P.D; c += 32) t0 = fmaf(P.x[b * P.x_sb + c], __ldg(P.W + label * P.D + c), t0);
+  return warp_sum(t0) + ((lab_ok && P.bias) ? P.bias[label] : 0.f) - logf(P.true_exp[b]);
+}
+
+__device__ __forceinline__ float ssm_sampled_logit(const SsmLogitParams& P, long long b, int j,
+                                                   long long label) {
+  float sv = P.logits[b * P.ld + j];
+  if (P.remove_hits && P.sampled[j] == label) sv += -FLT_MAX;
+  return sv + P.cs[j];
+}
+
+__global__ void __launch_bounds__(256) ssm_logits_fwd_kernel(const __grid_constant__ SsmLogitParams P) {
+  const int lane = threadIdx.x & 31;
+  const long long b = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  if (b >= P.B) return;
+  bool lab_ok;
+  const float t0 = ssm_true_logit(P, b, lane, lab_ok);
+  if (!lab_ok && lane == 0 && P.err) atomicOr(P.err, 1);
+  const long long label = P.labels[b];
+  float m = -INFINITY, l = 0.f;
+  for (int j = lane; j < P.S; j += 32) {
+    const float sv = ssm_sampled_logit(P, b, j, label);
+    const float mn = fmaxf(m, sv);
+    l = l * expf(m - mn) + expf(sv - mn);
+    m = mn;
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {   // combine the lanes' (max, sum) pairs
+    const float mo = __shfl_xor_sync(0xffffffffu, m, o), lo = __shfl_xor_sync(0xffffffffu, l, o);
+    const float mn = fmaxf(m, mo);
+    l = (m == -INFINITY ? 0.f : l * expf(m - mn)) + (mo == -INFINITY ? 0.f : lo * expf(mo - mn));
+    m = mn;
+  }
+  if (lane == 0) {
+    const float mn = fmaxf(m, t0);
+    const float tot = (m == -INFINITY ? 0.f : l * expf(m - mn)) + expf(t0 - mn);
+    const float lse = mn + logf(tot);
+    P.lse[b] = lse;
+    P.loss[b] = lse - t0;
+  }
+}
+
+__global__ void __launch_bounds__(256) ssm_logits_bwd_kernel(const __grid_constant__ SsmLogitParams P) {
+  const int lane = threadIdx.x & 31;
+  const long long b = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  if (b >= P.B) return;
+  bool lab_ok;
+  const float t0 = ssm_true_logit(P, b, lane, lab_ok);
+  const long long label = P.labels[b];
+  const float lse = P.lse[b], g = P.gloss[b];
+  if (lane == 0) P.g0[b] = g * (expf(t0 - lse) - 1.f);
+  for (int j = lane; j < P.S; j += 32)
+    P.G1[b * P.g1_ld + j] = g * expf(ssm_sampled_logit(P, b, j, label) - lse);
+}
+
+// gx[b] += g0[b] * W[label[b]]  (the true class' share of d loss / d x; the sampled share is a GEMM)
+__global__ void __launch_bounds__(256) ssm_true_gx_kernel(const __grid_constant__ SsmLogitParams P) {
+  const int lane = threadIdx.x & 31;
+  const long long b = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  if (b >= P.B) return;
+  const long long label = P.labels[b];
+  if (label < 0 || label >= P.N) return;
+  const float g0 = P.g0[b];
+  for (int c = lane; c < P.D; c += 32)
+    P.gx[b * P.gx_sb + c] = fmaf(g0, __ldg(P.W + label * P.D + c), P.gx[b * P.gx_sb + c]);
+}
+
 template <bool BWD>
 static int ssm_launch(const SsmParams& P, cudaStream_t st) {
   const unsigned blocks = (unsigned)((P.B * 32 + 255) / 256);
@@ -314,4 +406,79 @@ extern "C" int rtf_sampled_softmax_bwd(const float* d_x, int64_t x_sb, const flo
   cudaStream_t st = (cudaStream_t)stream;
   ssm_gather<<<(unsigned)((S * 32 + 255) / 256), 256, 0, st>>>(P);
   return ssm_launch<true>(P, st);
+}
+
+// ---- GEMM form: pieces around x . Ws^T (the caller runs the GEMMs, e.g. rtf_dense_gemm_nt/nn/tn)
+extern "C" int rtf_ssm_gather(const float* d_W, const float* d_bias, const int64_t* d_sampled,
+                              const float* d_samp_exp, int64_t N, int S, int D, float* d_Ws,
+                              float* d_cs, int32_t* d_err, void* stream) {
+  if (N <= 0 || S <= 0 || D <= 0 || !d_W || !d_sampled || !d_samp_exp || !d_Ws || !d_cs)
+    return RTF_E_ARG;
+  SsmParams P = {};
+  P.W = d_W; P.bias = d_bias; P.sampled = (const long long*)d_sampled; P.samp_exp = d_samp_exp;
+  P.N = N; P.S = S; P.D = D; P.Ws = d_Ws; P.cs = d_cs; P.err = d_err;
+  ssm_gather<<<(unsigned)((S * 32 + 255) / 256), 256, 0, (cudaStream_t)stream>>>(P);
+  RTF_CHECK_LAUNCH();
+  return 0;
+}
+
+static int ssm_logit_fill(SsmLogitParams& P, const float* logits, int64_t ld, const float* x,
+                          int64_t x_sb, const float* W, const float* bias, const int64_t* labels,
+                          const int64_t* sampled, const float* te, const float* cs, int64_t B,
+                          int64_t N, int S, int D, int remove_hits) {
+  if (B < 0 || N <= 0 || S <= 0 || D <= 0 || ld < S) return RTF_E_ARG;
+  if (B == 0) return 0;
+  if (!logits || !x || !W || !labels || !sampled || !te || !cs) return RTF_E_ARG;
+  P.logits = logits; P.ld = ld; P.x = x; P.x_sb = x_sb; P.W = W; P.bias = bias;
+  P.labels = (const long long*)labels; P.sampled = (const long long*)sampled; P.true_exp = te;
+  P.cs = cs; P.B = B; P.N = N; P.S = S; P.D = D; P.remove_hits = remove_hits;
+  return 0;
+}
+
+extern "C" int rtf_ssm_logits_fwd(const float* d_logits, int64_t ld, const float* d_x, int64_t x_sb,
+                                  const float* d_W, const float* d_bias, const int64_t* d_labels,
+                                  const int64_t* d_sampled, const float* d_true_exp,
+                                  const float* d_cs, int64_t B, int64_t N, int S, int D,
+                                  int remove_hits, float* d_loss, float* d_lse, int32_t* d_err,
+                                  void* stream) {
+  SsmLogitParams P = {};
+  int rc = ssm_logit_fill(P, d_logits, ld, d_x, x_sb, d_W, d_bias, d_labels, d_sampled, d_true_exp,
+                          d_cs, B, N, S, D, remove_hits);
+  if (rc || B == 0) return rc;
+  if (!d_loss || !d_lse) return RTF_E_ARG;
+  P.loss = d_loss; P.lse = d_lse; P.err = d_err;
+  ssm_logits_fwd_kernel<<<(unsigned)((B * 32 + 255) / 256), 256, 0, (cudaStream_t)stream>>>(P);
+  RTF_CHECK_LAUNCH();
+  return 0;
+}
+
+extern "C" int rtf_ssm_logits_bwd(const float* d_logits, int64_t ld, const float* d_x, int64_t x_sb,
+                                  const float* d_W, const float* d_bias, const int64_t* d_labels,
+                                  const int64_t* d_sampled, const float* d_true_exp,
+                                  const float* d_cs, int64_t B, int64_t N, int S, int D,
+                                  int remove_hits, const float* d_lse, const float* d_gloss,
+                                  float* d_g0, float* d_G1, int64_t g1_ld, void* stream) {
+  SsmLogitParams P = {};
+  int rc = ssm_logit_fill(P, d_logits, ld, d_x, x_sb, d_W, d_bias, d_labels, d_sampled, d_true_exp,
+                          d_cs, B, N, S, D, remove_hits);
+  if (rc || B == 0) return rc;
+  if (!d_lse || !d_gloss || !d_g0 || !d_G1 || g1_ld < S) return RTF_E_ARG;
+  P.lse = const_cast<float*>(d_lse); P.gloss = d_gloss; P.g0 = d_g0; P.G1 = d_G1; P.g1_ld = g1_ld;
+  ssm_logits_bwd_kernel<<<(unsigned)((B * 32 + 255) / 256), 256, 0, (cudaStream_t)stream>>>(P);
+  RTF_CHECK_LAUNCH();
+  return 0;
+}
+
+extern "C" int rtf_ssm_true_gx(const float* d_W, const int64_t* d_labels, const float* d_g0,
+                               int64_t B, int64_t N, int D, float* d_gx, int64_t gx_sb,
+                               void* stream) {
+  if (B < 0 || N <= 0 || D <= 0) return RTF_E_ARG;
+  if (B == 0) return 0;
+  if (!d_W || !d_labels || !d_g0 || !d_gx) return RTF_E_ARG;
+  SsmLogitParams P = {};
+  P.W = d_W; P.labels = (const long long*)d_labels; P.g0 = const_cast<float*>(d_g0); P.B = B;
+  P.N = N; P.D = D; P.gx = d_gx; P.gx_sb = gx_sb;
+  ssm_true_gx_kernel<<<(unsigned)((B * 32 + 255) / 256), 256, 0, (cudaStream_t)stream>>>(P);
+  RTF_CHECK_LAUNCH();
+  return 0;
 }

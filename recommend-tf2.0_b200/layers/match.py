@@ -207,6 +207,84 @@ class _SampledSoftmaxFn(torch.autograd.Function):
         return gw, None, None, gx, None, None, None, None, None, None
 
 
+class _SampledSoftmaxGemmFn(torch.autograd.Function):
+    """K8 for large S: the (B, S) sampled logits are one tensor-core GEMM x . Ws^T
+    (rtf_dense_gemm_nt, fp32-accurate), the per-sample work (true logit, hit removal, log-sum-exp)
+    a streaming epilogue; backward = epilogue (g0, G1) + two GEMMs.  Same semantics as
+    _SampledSoftmaxFn (rtf_sampled_softmax_*), which re-streams the S rows per sample."""
+
+    @staticmethod
+    def forward(ctx, weights, biases, labels, inputs, sampled, true_exp, samp_exp, remove_hits, err,
+                table=None):
+        from ..core import dense_gemm
+        L.require_cuda(inputs, "sampled_softmax_loss(inputs)")
+        weights, inputs = weights.contiguous(), inputs.contiguous()
+        B, D = inputs.shape
+        N, S = weights.shape[0], sampled.numel()
+        dev = inputs.device
+        Ws = torch.empty((S, D), dtype=torch.float32, device=dev)
+        cs = torch.empty(S, dtype=torch.float32, device=dev)
+        bptr = None if biases is None else biases.data_ptr()
+        eptr = None if err is None else err.data_ptr()
+        L.check(L.lib().rtf_ssm_gather(weights.data_ptr(), bptr, sampled.data_ptr(), samp_exp.data_ptr(),
+                                       N, S, D, Ws.data_ptr(), cs.data_ptr(), eptr,
+                                       L.current_stream_ptr()), "rtf_ssm_gather")
+        logits = dense_gemm("nt", inputs, Ws)                        # (B, S)
+        loss = torch.empty(B, dtype=torch.float32, device=dev)
+        lse = torch.empty_like(loss)
+        rc = L.lib().rtf_ssm_logits_fwd(logits.data_ptr(), logits.stride(0), inputs.data_ptr(),
+                                        inputs.stride(0), weights.data_ptr(), bptr, labels.data_ptr(),
+                                        sampled.data_ptr(), true_exp.data_ptr(), cs.data_ptr(), B, N, S, D,
+                                        int(remove_hits), loss.data_ptr(), lse.data_ptr(), eptr,
+                                        L.current_stream_ptr())
+        L.check(rc, "rtf_ssm_logits_fwd")
+        ctx.save_for_backward(weights, inputs, labels, sampled, true_exp, logits, Ws, cs, lse)
+        ctx.biases, ctx.remove_hits, ctx.table = biases, remove_hits, table
+        return loss
+
+    @staticmethod
+    def backward(ctx, gloss):
+        from ..core import dense_gemm
+        weights, inputs, labels, sampled, true_exp, logits, Ws, cs, lse = ctx.saved_tensors
+        biases = ctx.biases
+        B, D = inputs.shape
+        N, S = weights.shape[0], sampled.numel()
+        gloss = gloss.contiguous()
+        g0 = torch.empty(B, dtype=torch.float32, device=inputs.device)
+        G1 = torch.empty((B, S), dtype=torch.float32, device=inputs.device)
+        rc = L.lib().rtf_ssm_logits_bwd(logits.data_ptr(), logits.stride(0), inputs.data_ptr(),
+                                        inputs.stride(0), weights.data_ptr(),
+                                        None if biases is None else biases.data_ptr(), labels.data_ptr(),
+                                        sampled.data_ptr(), true_exp.data_ptr(), cs.data_ptr(), B, N, S, D,
+                                        int(ctx.remove_hits), lse.data_ptr(), gloss.data_ptr(), g0.data_ptr(),
+                                        G1.data_ptr(), G1.stride(0), L.current_stream_ptr())
+        L.check(rc, "rtf_ssm_logits_bwd")
+        gx = dense_gemm("nn", G1, Ws)                                # sampled share of d loss / d x
+        L.check(L.lib().rtf_ssm_true_gx(weights.data_ptr(), labels.data_ptr(), g0.data_ptr(), B, N, D,
+                                        gx.data_ptr(), gx.stride(0), L.current_stream_ptr()),
+                "rtf_ssm_true_gx")
+        gw = None
+        fused = ctx.table is not None and ctx.table[0].optimizer is not None
+        if fused or ctx.needs_input_grad[0]:
+            # weight-row gradients: true rows g0*x (B,D), sampled rows G1^T x (S,D); K2 reduces them
+            # per touched row ([labels | sampled] may repeat), deterministically
+            rows = torch.cat([g0.unsqueeze(1) * inputs, dense_gemm("tn", G1, inputs)], 0)
+            ids = torch.cat([labels, sampled]).reshape(-1, 1)
+            if fused:
+                tset, t = ctx.table
+                tset.apply_sparse_grad(ids, [t], rows)
+            else:
+                keys, tot, _ = embed_bwd([weights], [0], ids, rows, "BF", None, want_unique=True)
+                gw = torch.zeros_like(weights)
+                gw[keys] = tot[:, :D]
+        return gw, None, None, gx, None, None, None, None, None, None
+
+
+def _gemm_form_ok(B, S, D) -> bool:
+    """The GEMM form pays from a few dozen sampled classes up (and needs 16-byte rows)."""
+    return S >= 32 and S % 4 == 0 and D % 4 == 0 and B % 4 == 0 and B >= 64
+
+
 def sampled_softmax_loss(weights, biases, labels, inputs, num_sampled, num_classes, num_true=1,
                          sampled_values=None, remove_accidental_hits=True, seed: int = 0,
                          err: Optional[torch.Tensor] = None, table=None):
@@ -227,8 +305,10 @@ def sampled_softmax_loss(weights, biases, labels, inputs, num_sampled, num_class
         sampled = sampled.reshape(-1).to(torch.int64).contiguous()
         true_exp = true_exp.reshape(-1).to(torch.float32).contiguous()
         samp_exp = samp_exp.reshape(-1).to(torch.float32).contiguous()
-    return _SampledSoftmaxFn.apply(weights, biases, labels, inputs, sampled, true_exp, samp_exp,
-                                   remove_accidental_hits, err, table)
+    fn = _SampledSoftmaxGemmFn if _gemm_form_ok(inputs.shape[0], sampled.numel(), inputs.shape[1]) \
+        else _SampledSoftmaxFn
+    return fn.apply(weights, biases, labels, inputs, sampled, true_exp, samp_exp,
+                    remove_accidental_hits, err, table)
 
 
 class SampledSoftmaxLayer(Layer):

@@ -288,7 +288,31 @@ def test_din_attention_quirks(rtf):
 
 
 # ------------------------------------------------------------------ sampled softmax (a11)
-@pytest.mark.parametrize("B,N,S,D", [(64, 1000, 5, 32), (128, 100000, 1024, 64), (17, 50, 20, 10)])
+def test_sampled_softmax_gemm_form_is_taken_and_matches_streaming_form(rtf):
+    """S >= 32: logits through the tensor-core GEMM + epilogues; same loss and gradients as the
+    streaming kernel (rtf_sampled_softmax_*)."""
+    from recommend_tf2_b200.layers import match as M
+    torch.manual_seed(3)
+    B, N, S, D = 256, 5000, 64, 16
+    W = (torch.randn(N, D, device="cuda") * 0.1)
+    x = torch.randn(B, D, device="cuda")
+    labels = torch.randint(0, N, (B,), device="cuda")
+    smp, tries = M.log_uniform_candidate_sampler(S, N, seed=3)
+    labels[:8] = smp[:8]
+    te, se = M.log_uniform_expected(labels, N, tries), M.log_uniform_expected(smp, N, tries)
+    res = []
+    for fn in (M._SampledSoftmaxGemmFn, M._SampledSoftmaxFn):
+        Wi, xi = W.clone().requires_grad_(True), x.clone().requires_grad_(True)
+        loss = fn.apply(Wi, None, labels, xi, smp, te, se, True, None, None)
+        loss.sum().backward()
+        res.append((loss.detach(), xi.grad, Wi.grad))
+    assert M._gemm_form_ok(B, S, D)
+    for a, b_ in zip(*res):
+        torch.testing.assert_close(a, b_, rtol=1e-5, atol=1e-6)
+
+
+@pytest.mark.parametrize("B,N,S,D", [(64, 1000, 5, 32), (128, 100000, 1024, 64), (17, 50, 20, 10),
+                                     (256, 5000, 64, 16)])
 def test_sampled_softmax_injected_samples(rtf, B, N, S, D):
     rng = np.random.default_rng(5)
     W = rng.normal(0, 0.1, (N, D)).astype(np.float32)
