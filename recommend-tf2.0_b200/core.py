@@ -344,13 +344,15 @@ class BatchNormalization(Layer):
         x2 = x.reshape(-1, shp[-1])
         if self.training:
             # Keras updates moving_variance with the BIASED batch variance (torch's running_var
-            # takes the unbiased one), so the moving statistics are kept here and the
-            # normalisation itself (batch statistics, biased variance) goes through F.batch_norm
+            # takes the unbiased one), so the moving statistics are kept here — from the batch
+            # statistics the normalisation kernel returns anyway (mean, 1/sqrt(var + eps)): no
+            # extra pass over the activations
+            y, mean, invstd = torch.native_batch_norm(x2, self.gamma, self.beta, None, None, True, 0.0,
+                                                      self.epsilon)
             with torch.no_grad():
-                var, mean = torch.var_mean(x2, dim=0, unbiased=False)
+                var = 1.0 / (invstd * invstd) - self.epsilon
                 self.moving_mean.mul_(self.momentum).add_(mean, alpha=1.0 - self.momentum)
                 self.moving_variance.mul_(self.momentum).add_(var, alpha=1.0 - self.momentum)
-            y = F.batch_norm(x2, None, None, self.gamma, self.beta, True, 0.0, self.epsilon)
         else:
             y = F.batch_norm(x2, self.moving_mean, self.moving_variance, self.gamma, self.beta,
                              False, 0.0, self.epsilon)
