@@ -82,7 +82,7 @@ def _worker(rank, world, port, F, D, B_local):
         dist.destroy_process_group()
 
 
-@pytest.mark.parametrize("world,F", [(2, 5), (2, 26), (3, 7)])
+@pytest.mark.parametrize("world,F", [(2, 5), (2, 26), (3, 7), (4, 26)])
 def test_exchange_round_trip_gloo(world, F):
     mp.spawn(_worker, args=(world, _free_port(), F, 4, 3), nprocs=world, join=True)
 
@@ -257,9 +257,9 @@ def _rep_worker(rank, world, port, kind):
         dist.destroy_process_group()
 
 
-@pytest.mark.parametrize("kind", ["adam", "adagrad", "sgd"])
-def test_replicated_tables_combine_and_update_gloo(kind):
-    mp.spawn(_rep_worker, args=(2, _free_port(), kind), nprocs=2, join=True)
+@pytest.mark.parametrize("world,kind", [(2, "adam"), (2, "adagrad"), (2, "sgd"), (4, "adam")])
+def test_replicated_tables_combine_and_update_gloo(world, kind):
+    mp.spawn(_rep_worker, args=(world, _free_port(), kind), nprocs=world, join=True)
 
 
 # ---- property test: any table list / world size gives a consistent placement -------------------
