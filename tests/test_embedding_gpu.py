@@ -122,6 +122,27 @@ def test_skip_invalid_leaves_rows_untouched_and_unflagged(rtf):
     assert int(err.item()) == 0
 
 
+@pytest.mark.parametrize("dims,frac_bad", [((128, 64, 256, 8), 0.875), ((512, 128), 0.5), ((16,), 0.99)])
+def test_skip_invalid_mixed_dims_mostly_foreign(rtf, dims, frac_bad):
+    """The holder-side gather of a row-wise sharded table: 7 of 8 lookups are foreign (-1)."""
+    g = torch.Generator(device="cuda").manual_seed(9)
+    B = 4099
+    rows = [1000 + 7 * i for i in range(len(dims))]
+    tabs = [torch.randn(n, d, device="cuda", generator=g) for n, d in zip(rows, dims)]
+    ids = torch.stack([torch.randint(0, n, (B,), device="cuda", generator=g) for n in rows], 1)
+    bad = torch.rand(B, len(dims), device="cuda", generator=g) < frac_bad
+    ids_bad = torch.where(bad, torch.full_like(ids, -1), ids).to(torch.int32)
+    out = torch.full((B, sum(dims)), -3.5, device="cuda")
+    rtf.embed_fwd(tabs, ids_bad, "BF", None, err=None, out=out, skip_invalid=True)
+    off = 0
+    for f, (t, d) in enumerate(zip(tabs, dims)):
+        got = out[:, off:off + d]
+        ok = ~bad[:, f]
+        assert torch.equal(got[ok], t[ids[ok, f]])
+        assert bool((got[~ok] == -3.5).all())
+        off += d
+
+
 def test_empty_batch(rtf):
     tab = torch.zeros(10, 8, device="cuda")
     ids = torch.zeros((0, 1), dtype=torch.int32, device="cuda")
