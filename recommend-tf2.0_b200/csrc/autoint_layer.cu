@@ -24,6 +24,8 @@
 //                                   CTA's samples (fixed grid, fixed order); the per-CTA
 //                                   partials are summed in CTA order by a second tiny kernel,
 // so the weight gradients are reproducible bit for bit.
+#include <cstdlib>
+
 #include "rtf_common.cuh"
 
 namespace rtf {
@@ -220,6 +222,146 @@ autoint_fwd_kernel(const __grid_constant__ AiParams P) {
       }
     }
     __syncthreads();  // Xs / Ms / Ps are overwritten by the next sample
+  }
+}
+
+// ---- forward, packed-FMA version (sm_100 FFMA2: two fp32 FMAs per issue slot) ----------------
+// The scalar version above is bound by the FMA pipe's issue rate (one FFMA per 2 cycles and
+// scheduler).  Here every contraction is arranged so that BOTH halves of a packed FMA are useful
+// and come out of the loads already paired:
+//   projections: X is staged TRANSPOSED (Xt[k][row]), one 128-bit broadcast load gives 4 rows of
+//                column k = two row pairs; {w,w} pairs live in registers for the whole launch;
+//   Q K^T:       K is written transposed by its projection (Kt[col][key]); a thread owns a query
+//                row, keeps its scores in REGISTERS (FP/2 float2) and adds {q_d,q_d} x {K_j,K_j+1};
+//   P V:         pairs over the head dimension come straight from V's rows, {p,p} is one move.
+// FP = compile-time bound on the field count (multiple of 4); softmax as in the scalar version.
+template <int DM, int HS, int HSZ, int FP>
+__global__ void __launch_bounds__(AI_THREADS, FP <= 40 ? 4 : 2)
+autoint_fwd2_kernel(const __grid_constant__ AiParams P) {
+  extern __shared__ __align__(16) float sm[];
+  constexpr int NC = (HS + 31) / 32;
+  const int F = P.F, H = P.H;
+  float* Xt = sm;                 // [DM][FP]   X transposed
+  float* Qt = Xt + DM * FP;       // [HS][FP]   Q transposed (lanes = query rows read it conflict-free)
+  float* Kt = Qt + FP * HS;       // [HS][FP]   K transposed
+  float* Vs = Kt + HS * FP;       // [FP][HS]
+  float* Rs = Vs + FP * HS;       // [FP][HS]
+  const int lane = threadIdx.x & 31, m = threadIdx.x >> 5;
+  const bool live = m < 3 || P.use_res;
+  float2 ww[NC][DM];              // {w,w} of this thread's weight column(s)
+#pragma unroll
+  for (int cc = 0; cc < NC; ++cc)
+#pragma unroll
+    for (int k = 0; k < DM; ++k) {
+      const int c = lane + 32 * cc;
+      const float w = (live && c < HS) ? __ldg(P.w[m] + k * HS + c) : 0.f;
+      ww[cc][k] = make_float2(w, w);
+    }
+  for (int e = threadIdx.x; e < DM * FP; e += AI_THREADS) Xt[e] = 0.f;   // pad rows stay zero
+  __syncthreads();
+  for (long long b = blockIdx.x; b < P.B; b += gridDim.x) {
+    const float* xg = P.x + b * F * DM;
+    for (int e = threadIdx.x; e < F * DM; e += AI_THREADS) {
+      const int r = e / DM, k = e - r * DM;
+      Xt[k * FP + r] = __ldg(xg + e);
+    }
+    __syncthreads();
+    // ---- projections: thread (matrix m, column c), rows in pairs
+    if (live) {
+#pragma unroll
+      for (int cc = 0; cc < NC; ++cc) {
+        const int c = lane + 32 * cc;
+        if (c >= HS) continue;
+        float* dst = m == 2 ? Vs : Rs;
+#pragma unroll 2
+        for (int r0 = 0; r0 < FP; r0 += 4) {
+          float2 a0 = make_float2(0.f, 0.f), a1 = make_float2(0.f, 0.f);
+#pragma unroll
+          for (int k = 0; k < DM; ++k) {
+            const float4 x4 = *reinterpret_cast<const float4*>(Xt + k * FP + r0);
+            a0 = __ffma2_rn(make_float2(x4.x, x4.y), ww[cc][k], a0);
+            a1 = __ffma2_rn(make_float2(x4.z, x4.w), ww[cc][k], a1);
+          }
+          const float v[4] = {ai_act(P.act, a0.x), ai_act(P.act, a0.y), ai_act(P.act, a1.x),
+                              ai_act(P.act, a1.y)};
+          if (m <= 1) {   // Q and K leave transposed
+            *reinterpret_cast<float4*>((m == 0 ? Qt : Kt) + c * FP + r0) =
+                make_float4(v[0], v[1], v[2], v[3]);
+          } else {
+#pragma unroll
+            for (int u = 0; u < 4; ++u)
+              if (r0 + u < F) dst[(r0 + u) * HS + c] = v[u];
+          }
+        }
+      }
+    }
+    __syncthreads();
+    // ---- attention: thread per (head, query row); scores in registers
+    for (int p = threadIdx.x; p < H * F; p += AI_THREADS) {
+      const int h = p / F, i = p - h * F;
+      float2 s2[FP / 2];
+#pragma unroll
+      for (int j = 0; j < FP / 2; ++j) s2[j] = make_float2(0.f, 0.f);
+#pragma unroll
+      for (int d = 0; d < HSZ; ++d) {
+        const float q = Qt[(h * HSZ + d) * FP + i];
+        const float2 qq = make_float2(q, q);
+        const float* kt = Kt + (h * HSZ + d) * FP;
+#pragma unroll
+        for (int j4 = 0; j4 < FP / 4; ++j4) {
+          const float4 k4 = *reinterpret_cast<const float4*>(kt + 4 * j4);
+          s2[2 * j4] = __ffma2_rn(qq, make_float2(k4.x, k4.y), s2[2 * j4]);
+          s2[2 * j4 + 1] = __ffma2_rn(qq, make_float2(k4.z, k4.w), s2[2 * j4 + 1]);
+        }
+      }
+      float mx = -INFINITY;
+#pragma unroll
+      for (int j = 0; j < FP / 2; ++j) {
+        s2[j].x = 2 * j < F ? s2[j].x * P.scale : -INFINITY;
+        s2[j].y = 2 * j + 1 < F ? s2[j].y * P.scale : -INFINITY;
+        mx = fmaxf(mx, fmaxf(s2[j].x, s2[j].y));
+      }
+      float sum = 0.f;
+#pragma unroll
+      for (int j = 0; j < FP / 2; ++j) {
+        s2[j].x = 2 * j < F ? expf(s2[j].x - mx) : 0.f;
+        s2[j].y = 2 * j + 1 < F ? expf(s2[j].y - mx) : 0.f;
+        sum += s2[j].x + s2[j].y;
+      }
+      const float inv = 1.f / sum;
+      float2 o2[HSZ / 2];
+#pragma unroll
+      for (int d = 0; d < HSZ / 2; ++d) o2[d] = make_float2(0.f, 0.f);
+      const float* V = Vs + h * HSZ;
+#pragma unroll
+      for (int j = 0; j < FP; ++j) {
+        if (j < F) {
+          const float pj = ((j & 1) ? s2[j >> 1].y : s2[j >> 1].x) * inv;
+          const float2 pp = make_float2(pj, pj);
+#pragma unroll
+          for (int d4 = 0; d4 < HSZ / 4; ++d4) {
+            const float4 vv = *reinterpret_cast<const float4*>(V + j * HS + 4 * d4);
+            o2[2 * d4] = __ffma2_rn(pp, make_float2(vv.x, vv.y), o2[2 * d4]);
+            o2[2 * d4 + 1] = __ffma2_rn(pp, make_float2(vv.z, vv.w), o2[2 * d4 + 1]);
+          }
+        }
+      }
+      float* dst = P.out + (b * F + i) * HS + h * HSZ;
+      const float* R = Rs + i * HS + h * HSZ;
+#pragma unroll
+      for (int d4 = 0; d4 < HSZ / 4; ++d4) {
+        float4 v = make_float4(o2[2 * d4].x, o2[2 * d4].y, o2[2 * d4 + 1].x, o2[2 * d4 + 1].y);
+        if (P.use_res) {
+          const float4 r = *reinterpret_cast<const float4*>(R + 4 * d4);
+          v.x = fmaxf(v.x + r.x, 0.f);
+          v.y = fmaxf(v.y + r.y, 0.f);
+          v.z = fmaxf(v.z + r.z, 0.f);
+          v.w = fmaxf(v.w + r.w, 0.f);
+        }
+        *reinterpret_cast<float4*>(dst + 4 * d4) = v;
+      }
+    }
+    __syncthreads();  // Xt / Qt / Kt / V / R are overwritten by the next sample
   }
 }
 
@@ -453,8 +595,30 @@ static int ai_grid(long long B, int per_sm) {
   return (int)(B < g ? B : g);
 }
 
+template <int DM, int HS, int HSZ, int FP>
+static int ai_launch_fwd2(const AiParams& P, cudaStream_t st) {
+  const size_t smem = ai_round16((size_t)DM * FP + 4 * (size_t)FP * HS);
+  if (smem > 227 * 1024) return RTF_E_RANGE;
+  cudaError_t e = cudaFuncSetAttribute(autoint_fwd2_kernel<DM, HS, HSZ, FP>,
+                                       cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  if (e != cudaSuccess) return (int)e;
+  int per_sm = (int)((227 * 1024) / (smem + 1024));
+  const int cap = FP <= 40 ? 4 : 2;
+  if (per_sm > cap) per_sm = cap;
+  if (per_sm < 1) per_sm = 1;
+  autoint_fwd2_kernel<DM, HS, HSZ, FP><<<ai_grid(P.B, per_sm), AI_THREADS, smem, st>>>(P);
+  RTF_CHECK_LAUNCH();
+  return 0;
+}
+
 template <int DM, int HS, int HSZ>
 static int ai_launch_fwd(const AiParams& P, cudaStream_t st) {
+  static const bool scalar = getenv("RTF_K6_SCALAR") != nullptr;   // comparison runs only
+  if (!scalar) {
+    if (P.F <= 16) return ai_launch_fwd2<DM, HS, HSZ, 16>(P, st);
+    if (P.F <= 40) return ai_launch_fwd2<DM, HS, HSZ, 40>(P, st);
+    return ai_launch_fwd2<DM, HS, HSZ, 64>(P, st);
+  }
   const size_t smem = ai_fwd_smem<DM, HS>(P.F, P.H);
   if (smem > 227 * 1024) return RTF_E_RANGE;
   cudaError_t e = cudaFuncSetAttribute(autoint_fwd_kernel<DM, HS, HSZ>,
