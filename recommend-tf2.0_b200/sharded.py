@@ -710,7 +710,6 @@ class PeerShardedDLRM(Layer):
         self.async_update = False       # set by ShardedDLRMTrainer: K2 behind the MLP backward
         self._xstream = None            # exchange stream: K1 + barrier + row pull, barrier + K2
         self._loc_cache = {}
-        self._rstream = None            # replicated tables' update chain
         self._prefetched = None         # exchange of a batch announced with prefetch()
         self._upd_ev = None
         # replicated block: the shards of rep_fields are contiguous at the end of the table buffer
@@ -890,26 +889,13 @@ class PeerShardedDLRM(Layer):
         Bl = self._grad_B
         Bg = Bl * self.world
         grad = self._grad_buf[: Bg * (Ts + Tr) * D].view(Bg, (Ts + Tr) * D)
-        # the replicated tables' chain (reduce-only K2 over MY samples' rows -> dense all-reduce ->
-        # identical row update) needs no remote data: it runs on its own stream beside the barrier
-        # and the sharded tables' K2 instead of in front of them
-        cur = torch.cuda.current_stream()
-        rs = None
-        if Tr:
-            if self._rstream is None:
-                self._rstream = torch.cuda.Stream()
-            rs = self._rstream
-            rs.wait_stream(cur)
-            with torch.cuda.stream(rs):
-                rep = self._reduce_replicated(grad[self.rank * Bl: (self.rank + 1) * Bl, Ts * D:])
+        rep = self._reduce_replicated(grad[self.rank * Bl: (self.rank + 1) * Bl, Ts * D:]) if Tr else None
         self._grad_hdl.barrier(channel=0)
         self._out_inflight = False      # every peer is past its K4 forward (it has pushed its dX)
         if Ts:
             self.embed_layers.apply_prepared(self._prepared, grad)
-        if Tr:
-            with torch.cuda.stream(rs):
-                self._apply_replicated(*rep)
-            cur.wait_stream(rs)         # the next K1 reads the replicated rows
+        if rep is not None:
+            self._apply_replicated(*rep)
         self._pending, self._prepared = False, None
 
     # ---- replicated (data-parallel) tables
