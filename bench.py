@@ -70,6 +70,9 @@ def parse_args():
     ap.add_argument("--no-parity-check", action="store_true",
                     help="skip the untimed sharded-vs-single-GPU self-check run before a multi-GPU measurement")
     ap.add_argument("--no-kernel-timing", action="store_true")
+    ap.add_argument("--cuda-graph", default="auto", choices=["auto", "on", "off"],
+                    help="replay the training step from a CUDA graph (core.StepGraph). auto = on for "
+                         "the launch-bound workloads (fm, din, autoint, youtubednn), off elsewhere")
     return ap.parse_args()
 
 
@@ -657,6 +660,8 @@ def run_workload(args):
     wl = BW.WORKLOADS[args.workload]()
     B = wl.batch
     K, W = args.steps, max(args.warmup, 3)
+    wl.cuda_graph = wl.graphable and (args.cuda_graph == "on" or
+                                      (args.cuda_graph == "auto" and args.workload in GRAPH_AUTO))
     st = wl.build(pkg)
     rng = np.random.default_rng(1000 + rank)
     host = [tuple(torch.from_numpy(np.ascontiguousarray(a)).pin_memory() for a in wl.host_batch(rng, B))
@@ -669,6 +674,10 @@ def run_workload(args):
             dist.barrier()
         torch.cuda.synchronize()
 
+    if wl.cuda_graph:       # the eager steps + the capture happen before the W warm-up steps
+        for i in range(4):
+            st.step(*dev[i % W])
+        assert st.trainer.graph.graph is not None
     sampler = ClockSampler(local_rank) if rank == 0 else None
     for i in range(W):
         st.step(*dev[i])
@@ -727,9 +736,15 @@ def run_workload(args):
                         "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 4, "ms_per_step": ms_e2e / K},
                 "gpu_launches": (per_step or 0) * K * world, "roofline": roof, "cpu_baseline": cpu,
                 "final_loss": float(loss_host[-1])}
+        line["config"]["cuda_graph"] = (
+            "step replayed from one CUDA graph (inputs copied into static buffers, Adam step size "
+            "read from a device scalar)" if wl.cuda_graph else "off (eager launches)")
         print(json.dumps(line), flush=True)
     if world > 1:
         dist.destroy_process_group()
+
+
+GRAPH_AUTO = ("fm", "din", "autoint", "youtubednn")
 
 
 class _StepShim:

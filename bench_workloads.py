@@ -30,6 +30,8 @@ class Workload:
     metric = ""
     batch = 0
     cpu_batch = 0
+    cuda_graph = False        # set by bench.py --cuda-graph: replay the step from a CUDA graph
+    graphable = True          # False: the step draws a host-side value every step
 
     def config(self):
         raise NotImplementedError
@@ -79,7 +81,8 @@ class FM(Workload):
         import torch
         fc = pkg.criteo_feature_columns(self.K, rows=CRITEO_ROWS)
         m = pkg.FMModel(fc, k=self.K, seed=1)
-        tr = pkg.models.Trainer(m, lambda out, y: pkg.layers.binary_crossentropy(y, out), embed_l2=1e-4)
+        tr = pkg.models.Trainer(m, lambda out, y: pkg.layers.binary_crossentropy(y, out), embed_l2=1e-4,
+                                cuda_graph=self.cuda_graph)
         return _Stepper(tr, lambda b: ([b[0], b[1]], b[2]))
 
     def host_batch(self, rng, B, cpu=False):
@@ -125,7 +128,8 @@ class DIN(Workload):
 
     def build(self, pkg):
         m = pkg.models.DIN([self.ITEMS, self.CATES], embed_dim=self.D, maxlen=self.L, seed=1)
-        tr = pkg.models.Trainer(m, lambda out, y: pkg.layers.binary_crossentropy(y, out), embed_l2=1e-4)
+        tr = pkg.models.Trainer(m, lambda out, y: pkg.layers.binary_crossentropy(y, out), embed_l2=1e-4,
+                                cuda_graph=self.cuda_graph)
         return _Stepper(tr, lambda b: ([b[0], b[1]], b[2]))
 
     def host_batch(self, rng, B, cpu=False):
@@ -175,7 +179,8 @@ class AutoInt(Workload):
     def build(self, pkg):
         fc = pkg.criteo_feature_columns(self.D, rows=CRITEO_ROWS)
         m = pkg.models.AutoInt(fc, self.HS, self.H, self.NL, use_res=True, seed=1)
-        tr = pkg.models.Trainer(m, lambda out, y: pkg.layers.binary_crossentropy(y, out), embed_l2=1e-4)
+        tr = pkg.models.Trainer(m, lambda out, y: pkg.layers.binary_crossentropy(y, out), embed_l2=1e-4,
+                                cuda_graph=self.cuda_graph)
         return _Stepper(tr, lambda b: ([b[0], b[1]], b[2]))
 
     def host_batch(self, rng, B, cpu=False):
@@ -219,7 +224,7 @@ class SASRec(Workload):
 
     def build(self, pkg):
         m = pkg.models.SASRec(self.ITEMS, self.D, blocks=2, num_heads=1, seq_len=self.L, neg_len=self.NEG, seed=1)
-        tr = pkg.models.Trainer(m, lambda out, y: out[1])
+        tr = pkg.models.Trainer(m, lambda out, y: out[1], cuda_graph=self.cuda_graph)
         return _Stepper(tr, lambda b: ([b[0], b[1], b[2]], None))
 
     def host_batch(self, rng, B, cpu=False):
@@ -267,7 +272,7 @@ class YoutubeDNN(Workload):
     def build(self, pkg):
         m = pkg.models.YoutubeDNN(self.USER_FEATS, self.ITEMS, self.D, (64, self.D), num_sampled=self.S,
                                   conventional=True, sparse_optimizer=pkg.SparseOptimizer("adam", lr=1e-3), seed=1)
-        tr = pkg.models.Trainer(m, lambda out, y: out.mean())         # loss_util.sampledsoftmaxloss
+        tr = pkg.models.Trainer(m, lambda out, y: out.mean(), cuda_graph=self.cuda_graph)         # loss_util.sampledsoftmaxloss
         return _Stepper(tr, lambda b: ([b[0], b[1]], None))
 
     def host_batch(self, rng, B, cpu=False):

@@ -58,6 +58,10 @@ typedef struct rtf_opt {
   float beta2;
   float eps;
   float l2;
+  /* optional DEVICE scalar: when non-NULL the kernels read the step size from *lr_dev instead of
+   * `lr` — the Adam step size changes every step (bias corrections), so a training step captured
+   * in a CUDA graph must not have it baked into the launch parameters */
+  const float* lr_dev;
 } rtf_opt;
 
 /* library / build identification: returns the sm arch the kernels were built for (100) */
@@ -282,6 +286,10 @@ int rtf_din_attn_bwd(const float* d_q, int64_t q_sb, const float* d_k, int64_t k
 int rtf_log_uniform_workspace(int S, size_t* bytes);
 int rtf_log_uniform_sample(uint64_t seed, int S, int64_t range_max, int64_t* d_sampled,
                            int32_t* d_num_tries, void* d_ws, void* stream);
+/* same, the seed read from device memory at execution time (a step replayed from a CUDA graph
+ * draws fresh candidates every replay: the host bumps *d_seed between replays)             */
+int rtf_log_uniform_sample_dseed(const uint64_t* d_seed, int S, int64_t range_max,
+                                 int64_t* d_sampled, int32_t* d_num_tries, void* d_ws, void* stream);
 int rtf_log_uniform_expected(const int64_t* d_ids, int64_t n, int64_t range_max,
                              const int32_t* d_num_tries, float* d_out, void* stream);
 int rtf_sampled_softmax_workspace(int S, int D, size_t* bytes);

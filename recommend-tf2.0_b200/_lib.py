@@ -27,7 +27,8 @@ class RtfError(RuntimeError):
 
 class rtf_opt(C.Structure):
     _fields_ = [("kind", C.c_int32), ("lr", C.c_float), ("beta1", C.c_float),
-                ("beta2", C.c_float), ("eps", C.c_float), ("l2", C.c_float)]
+                ("beta2", C.c_float), ("eps", C.c_float), ("l2", C.c_float),
+                ("lr_dev", C.c_void_p)]
 
 
 _p = C.c_void_p
@@ -111,6 +112,7 @@ SIGNATURES = {
                          _p, _i64, _p, _i64, _p, _i64, _p, _i64, _p, _p],
     "rtf_log_uniform_workspace": [_int, C.POINTER(C.c_size_t)],
     "rtf_log_uniform_sample": [C.c_uint64, _int, _i64, _p, _p, _p, _p],
+    "rtf_log_uniform_sample_dseed": [_p, _int, _i64, _p, _p, _p, _p],
     "rtf_log_uniform_expected": [_p, _i64, _i64, _p, _p, _p],
     "rtf_sampled_softmax_workspace": [_int, _int, C.POINTER(C.c_size_t)],
     "rtf_sampled_softmax_fwd": [_p, _i64, _p, _p, _p, _p, _p, _p, _i64, _i64, _int, _int, _int,

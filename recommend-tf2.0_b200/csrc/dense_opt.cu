@@ -13,25 +13,27 @@
 
 namespace rtf {
 
-__device__ __forceinline__ void adam_elem(const rtf_opt& o, float g, float& w, float& a, float& b) {
+__device__ __forceinline__ void adam_elem(const rtf_opt& o, float lr, float g, float& w, float& a,
+                                          float& b) {
   a = __fadd_rn(__fmul_rn(o.beta1, a), __fmul_rn(__fsub_rn(1.0f, o.beta1), g));
   b = __fadd_rn(__fmul_rn(o.beta2, b), __fmul_rn(__fsub_rn(1.0f, o.beta2), __fmul_rn(g, g)));
-  w = __fsub_rn(w, __fdiv_rn(__fmul_rn(o.lr, a), __fadd_rn(__fsqrt_rn(b), o.eps)));
+  w = __fsub_rn(w, __fdiv_rn(__fmul_rn(lr, a), __fadd_rn(__fsqrt_rn(b), o.eps)));
 }
 
 __global__ void __launch_bounds__(256)
 dense_adam_kernel(float* __restrict__ w, const float* __restrict__ g, float* __restrict__ m,
                   float* __restrict__ v, long long n4, const __grid_constant__ rtf_opt o) {
+  const float lr = o.lr_dev ? __ldg(o.lr_dev) : o.lr;   // device scalar under CUDA-graph replay
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n4;
        i += (long long)gridDim.x * blockDim.x) {
     float4 wv = reinterpret_cast<float4*>(w)[i];
     const float4 gv = reinterpret_cast<const float4*>(g)[i];
     float4 mv = reinterpret_cast<float4*>(m)[i];
     float4 vv = reinterpret_cast<float4*>(v)[i];
-    adam_elem(o, gv.x, wv.x, mv.x, vv.x);
-    adam_elem(o, gv.y, wv.y, mv.y, vv.y);
-    adam_elem(o, gv.z, wv.z, mv.z, vv.z);
-    adam_elem(o, gv.w, wv.w, mv.w, vv.w);
+    adam_elem(o, lr, gv.x, wv.x, mv.x, vv.x);
+    adam_elem(o, lr, gv.y, wv.y, mv.y, vv.y);
+    adam_elem(o, lr, gv.z, wv.z, mv.z, vv.z);
+    adam_elem(o, lr, gv.w, wv.w, mv.w, vv.w);
     reinterpret_cast<float4*>(w)[i] = wv;
     reinterpret_cast<float4*>(m)[i] = mv;
     reinterpret_cast<float4*>(v)[i] = vv;
@@ -46,6 +48,7 @@ rows_apply_dense_kernel(float* __restrict__ W, float* __restrict__ s1, float* __
   const long long gid = ((long long)blockIdx.x * blockDim.x + threadIdx.x) / lanes;
   const int lg = (int)(threadIdx.x % lanes);
   if (gid >= R || touched[gid] <= 0.f) return;
+  const float lr = o.lr_dev ? __ldg(o.lr_dev) : o.lr;
   const float two_l2 = __fmul_rn(2.0f, o.l2);
   for (int c = lg * 4; c < D; c += lanes * 4) {
     const long long off = gid * D + c;
@@ -67,12 +70,12 @@ rows_apply_dense_kernel(float* __restrict__ W, float* __restrict__ s1, float* __
       float g = gq[e];
       if (o.l2 > 0.f) g = __fadd_rn(g, __fmul_rn(two_l2, wq[e]));
       if (o.kind == RTF_OPT_SGD) {
-        wq[e] = __fsub_rn(wq[e], __fmul_rn(o.lr, g));
+        wq[e] = __fsub_rn(wq[e], __fmul_rn(lr, g));
       } else if (o.kind == RTF_OPT_ADAGRAD) {
         aq[e] = __fadd_rn(aq[e], __fmul_rn(g, g));
-        wq[e] = __fsub_rn(wq[e], __fdiv_rn(__fmul_rn(o.lr, g), __fadd_rn(__fsqrt_rn(aq[e]), o.eps)));
+        wq[e] = __fsub_rn(wq[e], __fdiv_rn(__fmul_rn(lr, g), __fadd_rn(__fsqrt_rn(aq[e]), o.eps)));
       } else {
-        adam_elem(o, g, wq[e], aq[e], bq[e]);
+        adam_elem(o, lr, g, wq[e], aq[e], bq[e]);
       }
     }
     *reinterpret_cast<float4*>(W + off) = make_float4(wq[0], wq[1], wq[2], wq[3]);

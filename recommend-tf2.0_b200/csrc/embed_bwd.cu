@@ -482,6 +482,7 @@ __device__ __forceinline__ void finish_row(const BwdParams& P, uint32_t key, uin
   }
   const rtf_opt& o = P.opt;
   if (o.kind == RTF_OPT_NONE) return;
+  const float lr = o.lr_dev ? __ldg(o.lr_dev) : o.lr;   // device scalar under CUDA-graph replay
   float* w = P.w[t] + row * dim;
   float* s1 = P.s1[t] ? P.s1[t] + row * dim : nullptr;
   float* s2 = P.s2[t] ? P.s2[t] + row * dim : nullptr;
@@ -498,16 +499,16 @@ __device__ __forceinline__ void finish_row(const BwdParams& P, uint32_t key, uin
       float g = acc[k].v[e];
       if (o.l2 > 0.f) g = __fadd_rn(g, __fmul_rn(two_l2, wv.v[e]));
       if (o.kind == RTF_OPT_SGD) {
-        wv.v[e] = __fsub_rn(wv.v[e], __fmul_rn(o.lr, g));
+        wv.v[e] = __fsub_rn(wv.v[e], __fmul_rn(lr, g));
       } else if (o.kind == RTF_OPT_ADAGRAD) {
         a.v[e] = __fadd_rn(a.v[e], __fmul_rn(g, g));
-        wv.v[e] = __fsub_rn(wv.v[e], __fdiv_rn(__fmul_rn(o.lr, g),
+        wv.v[e] = __fsub_rn(wv.v[e], __fdiv_rn(__fmul_rn(lr, g),
                                                __fadd_rn(__fsqrt_rn(a.v[e]), o.eps)));
       } else {  // Adam (Keras form; lr already carries the bias corrections)
         a.v[e] = __fadd_rn(__fmul_rn(o.beta1, a.v[e]), __fmul_rn(__fsub_rn(1.0f, o.beta1), g));
         b.v[e] = __fadd_rn(__fmul_rn(o.beta2, b.v[e]),
                            __fmul_rn(__fsub_rn(1.0f, o.beta2), __fmul_rn(g, g)));
-        wv.v[e] = __fsub_rn(wv.v[e], __fdiv_rn(__fmul_rn(o.lr, a.v[e]),
+        wv.v[e] = __fsub_rn(wv.v[e], __fdiv_rn(__fmul_rn(lr, a.v[e]),
                                                __fadd_rn(__fsqrt_rn(b.v[e]), o.eps)));
       }
     }
@@ -739,7 +740,7 @@ static int embed_bwd_impl(int phase, float* const* weights, float* const* state1
                           float* d_uniq_grad, int32_t* d_num_uniq, int* row_bits_out,
                           void* d_workspace, size_t workspace_bytes, void* stream) {
   using namespace rtf;
-  static const rtf_opt kNoOpt = {RTF_OPT_NONE, 0.f, 0.f, 0.f, 0.f, 0.f};
+  static const rtf_opt kNoOpt = {RTF_OPT_NONE, 0.f, 0.f, 0.f, 0.f, 0.f, nullptr};
   static float* const kNoPtrs[RTF_MAX_FIELDS] = {};
   if (!(phase & 2)) {
     opt = &kNoOpt;

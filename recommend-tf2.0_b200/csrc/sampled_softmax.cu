@@ -35,10 +35,12 @@ __device__ __forceinline__ uint64_t splitmix64(uint64_t x) {
 // sequential rejection loop of App. A14 yields for this RNG stream; the set lives in shared
 // memory when it fits (global-memory probes on one thread cost 465 us for S = 1024, this 25 us).
 __global__ void __launch_bounds__(32)
-log_uniform_sample_kernel(uint64_t seed, int S, long long range_max, long long* __restrict__ out,
+log_uniform_sample_kernel(uint64_t seed, const uint64_t* __restrict__ seed_dev, int S,
+                          long long range_max, long long* __restrict__ out,
                           int32_t* __restrict__ num_tries, long long* __restrict__ gtable, int cap,
                           int use_smem) {
   extern __shared__ long long stab[];
+  if (seed_dev) seed = *seed_dev;     // per-step seed of a CUDA-graph replay lives in memory
   long long* table = use_smem ? stab : gtable;
   const int lane = threadIdx.x;
   for (int i = lane; i < cap; i += 32) table[i] = -1;
@@ -324,8 +326,9 @@ extern "C" int rtf_log_uniform_workspace(int S, size_t* bytes) {
   return 0;
 }
 
-extern "C" int rtf_log_uniform_sample(uint64_t seed, int S, int64_t range_max, int64_t* d_sampled,
-                                      int32_t* d_num_tries, void* d_ws, void* stream) {
+static int log_uniform_sample_launch(uint64_t seed, const uint64_t* d_seed, int S, int64_t range_max,
+                                     int64_t* d_sampled, int32_t* d_num_tries, void* d_ws,
+                                     void* stream) {
   if (S <= 0 || range_max <= 0 || !d_sampled || !d_num_tries || !d_ws) return RTF_E_ARG;
   if ((int64_t)S > range_max) return RTF_E_RANGE;  // TF would never terminate (A14)
   int cap = 64;
@@ -338,9 +341,22 @@ extern "C" int rtf_log_uniform_sample(uint64_t seed, int S, int64_t range_max, i
     if (e != cudaSuccess) return (int)e;
   }
   log_uniform_sample_kernel<<<1, 32, use_smem ? smem : 0, (cudaStream_t)stream>>>(
-      seed, S, range_max, (long long*)d_sampled, d_num_tries, (long long*)d_ws, cap, use_smem);
+      seed, d_seed, S, range_max, (long long*)d_sampled, d_num_tries, (long long*)d_ws, cap,
+      use_smem);
   RTF_CHECK_LAUNCH();
   return 0;
+}
+
+extern "C" int rtf_log_uniform_sample(uint64_t seed, int S, int64_t range_max, int64_t* d_sampled,
+                                      int32_t* d_num_tries, void* d_ws, void* stream) {
+  return log_uniform_sample_launch(seed, nullptr, S, range_max, d_sampled, d_num_tries, d_ws, stream);
+}
+
+extern "C" int rtf_log_uniform_sample_dseed(const uint64_t* d_seed, int S, int64_t range_max,
+                                            int64_t* d_sampled, int32_t* d_num_tries, void* d_ws,
+                                            void* stream) {
+  if (!d_seed) return RTF_E_ARG;
+  return log_uniform_sample_launch(0, d_seed, S, range_max, d_sampled, d_num_tries, d_ws, stream);
 }
 
 extern "C" int rtf_log_uniform_expected(const int64_t* d_ids, int64_t n, int64_t range_max,

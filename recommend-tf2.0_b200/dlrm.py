@@ -14,7 +14,7 @@ import torch
 
 from .embedding import EmbeddingTables, SparseOptimizer
 from .interaction import dot_out_cols, embed_dot
-from .core import DNN, Dense, DenseAdam, Layer, binary_crossentropy
+from .core import DNN, Dense, DenseAdam, Layer, StepGraph, binary_crossentropy
 
 
 class DLRM(Layer):
@@ -76,24 +76,40 @@ class DLRMTrainer:
     optimizer on the tables), dense Adam on the MLPs (Keras form, core.DenseAdam: one
     rtf_dense_adam launch over the flat parameter buffer)."""
 
-    def __init__(self, model: DLRM, lr: float = 1e-3):
+    def __init__(self, model: DLRM, lr: float = 1e-3, cuda_graph: bool = False):
         self.model = model
         if model.embed_layers.optimizer is None:
             model.embed_layers.set_optimizer(SparseOptimizer("adam", lr=lr, l2=model.embed_reg))
         self.dense_opt = None
         self.lr = lr
-        model.embed_layers.async_update = True     # step() ends with wait_pending()
+        model.embed_layers.async_update = True     # the step ends with wait_pending()
+        # cuda_graph: replay the step from a CUDA graph (core.StepGraph); pays off when the step is
+        # launch-bound (small batches) — at batch 65536 the GPU is the bound and it changes nothing
+        self.graph = StepGraph(self._body, self._advance) if cuda_graph else None
+
+    def _advance(self):
+        self.model.embed_layers.begin_step()
+        self.dense_opt.advance()
+
+    def _body(self, inputs, labels):
+        m = self.model
+        pred = m(inputs)
+        loss = binary_crossentropy(labels, pred)
+        self.dense_opt.zero_grad()
+        loss.backward()
+        self.dense_opt.apply()
+        m.embed_layers.wait_pending()   # K2's row update ran on the side stream behind the MLP backward
+        return loss.detach()
 
     def step(self, dense, sparse, labels) -> torch.Tensor:
         m = self.model
         if self.dense_opt is None:      # layers build on first call: build them, then flatten
             build_dense_layers(m, dense.shape[1], dense.device)
             self.dense_opt = DenseAdam(m.dense_parameters(), lr=self.lr)
-        m.embed_layers.begin_step()
-        pred = m([dense, sparse])
-        loss = binary_crossentropy(labels, pred)
-        self.dense_opt.zero_grad()
-        loss.backward()
-        self.dense_opt.step()
-        m.embed_layers.wait_pending()   # K2's row update ran on the side stream behind the MLP backward
-        return loss.detach()
+            if self.graph is not None:
+                self.dense_opt.enable_device_lr()
+                m.embed_layers.optimizer.enable_device_lr(dense.device)
+        if self.graph is not None:
+            return self.graph([dense, sparse], labels)
+        self._advance()
+        return self._body([dense, sparse], labels)

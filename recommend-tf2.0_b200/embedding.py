@@ -35,12 +35,31 @@ class SparseOptimizer:
             raise ValueError(f"unknown sparse optimizer {kind!r}")
         self.kind, self.lr, self.beta1, self.beta2, self.eps, self.l2 = kind, lr, beta1, beta2, eps, l2
         self.step = 0
+        self.lr_dev: Optional[torch.Tensor] = None
+
+    def lr_for_step(self, step: int) -> float:
+        if self.kind == "adam":  # Keras folds both bias corrections into the step size
+            return self.lr * math.sqrt(1.0 - self.beta2 ** step) / (1.0 - self.beta1 ** step)
+        return self.lr
 
     def struct_for_step(self, step: int) -> L.rtf_opt:
-        lr = self.lr
-        if self.kind == "adam":  # Keras folds both bias corrections into the step size
-            lr = self.lr * math.sqrt(1.0 - self.beta2 ** step) / (1.0 - self.beta1 ** step)
-        return L.rtf_opt(_OPT[self.kind], lr, self.beta1, self.beta2, self.eps, self.l2)
+        return L.rtf_opt(_OPT[self.kind], self.lr_for_step(step), self.beta1, self.beta2, self.eps,
+                         self.l2, None if self.lr_dev is None else self.lr_dev.data_ptr())
+
+    def enable_device_lr(self, device):
+        """Keep the step size in a device scalar (rtf_opt.lr_dev) refreshed by advance(): K2 then
+        reads it from memory instead of its launch parameters, which is what lets a whole training
+        step be replayed from a CUDA graph (core.StepGraph) while Adam's bias-corrected step size
+        keeps changing.  The value is the same fp32 number the host path passes."""
+        if self.lr_dev is None:
+            self.lr_dev = torch.zeros(1, dtype=torch.float32, device=device)
+            self.lr_dev.fill_(self.lr_for_step(max(self.step, 1)))
+
+    def advance(self):
+        """Next training step: bump the counter and refresh the device step size, if enabled."""
+        self.step += 1
+        if self.lr_dev is not None:
+            self.lr_dev.fill_(self.lr_for_step(self.step))
 
     @property
     def n_states(self) -> int:
@@ -137,7 +156,7 @@ def embed_bwd(weights: Sequence[torch.Tensor], field_table: Sequence[int], ids: 
         ug = torch.zeros((cap, dim_max), dtype=torch.float32, device=ids.device)
         nu = torch.zeros(1, dtype=torch.int32, device=ids.device)
     if opt is None:
-        opt = L.rtf_opt(L.OPT_NONE, 0.0, 0.0, 0.0, 0.0, 0.0)
+        opt = L.rtf_opt(L.OPT_NONE, 0.0, 0.0, 0.0, 0.0, 0.0, None)
     row_bits = C.c_int(0)
     gsb = grad.stride(0) if grad.dim() >= 2 and B > 0 else 0
     rc = lib.rtf_embed_bwd(_ptr_array(weights),
@@ -241,7 +260,7 @@ class EmbeddingTables(torch.nn.Module):
     def begin_step(self):
         """Advance the optimizer's step counter (call once per training step before backward)."""
         if self.optimizer is not None:
-            self.optimizer.step += 1
+            self.optimizer.advance()
 
     def lookup(self, ids: torch.Tensor, field_table: Optional[Sequence[int]] = None,
                layout: str = "BF", pool: Optional[str] = None) -> torch.Tensor:
@@ -291,7 +310,7 @@ class EmbeddingTables(torch.nn.Module):
         lib = L.lib()
         opt = self.optimizer
         if reduce_only is not None:
-            st = L.rtf_opt(L.OPT_NONE, 0.0, 0.0, 0.0, 0.0, 0.0)
+            st = L.rtf_opt(L.OPT_NONE, 0.0, 0.0, 0.0, 0.0, 0.0, None)
         else:
             st = opt.struct_for_step(max(opt.step, 1))
         wl = self.wlist()

@@ -119,14 +119,25 @@ class PoolingLayer(Layer):
 
 
 # ------------------------------------------------------------------------------ sampled softmax
-def log_uniform_candidate_sampler(num_sampled: int, range_max: int, seed: int, device="cuda"):
+def log_uniform_candidate_sampler(num_sampled: int, range_max: int, seed, device="cuda"):
     """Device log-uniform (Zipfian) sampler with unique=True (App. A14).  Returns
-    (sampled int64 (S), num_tries int32 (1)); expected counts via `log_uniform_expected`."""
+    (sampled int64 (S), num_tries int32 (1)); expected counts via `log_uniform_expected`.
+    `seed`: a Python int, or a 1-element int64 CUDA tensor read at execution time (a step replayed
+    from a CUDA graph bumps it between replays)."""
     nb = C.c_size_t(0)
     L.check(L.lib().rtf_log_uniform_workspace(num_sampled, C.byref(nb)), "rtf_log_uniform_workspace")
     ws = torch.empty(nb.value, dtype=torch.uint8, device=device)
     sampled = torch.empty(num_sampled, dtype=torch.int64, device=device)
     tries = torch.zeros(1, dtype=torch.int32, device=device)
+    if isinstance(seed, torch.Tensor):
+        L.require_cuda(seed, "log_uniform_candidate_sampler(seed)")
+        if seed.dtype != torch.int64 or seed.numel() != 1:
+            raise TypeError("device seed must be one int64")
+        L.check(L.lib().rtf_log_uniform_sample_dseed(seed.data_ptr(), num_sampled, range_max,
+                                                     sampled.data_ptr(), tries.data_ptr(),
+                                                     ws.data_ptr(), L.current_stream_ptr()),
+                "rtf_log_uniform_sample_dseed")
+        return sampled, tries
     L.check(L.lib().rtf_log_uniform_sample(seed & 0xFFFFFFFFFFFFFFFF, num_sampled, range_max,
                                            sampled.data_ptr(), tries.data_ptr(), ws.data_ptr(),
                                            L.current_stream_ptr()), "rtf_log_uniform_sample")

@@ -240,16 +240,30 @@ class YoutubeDNN(Layer):
         self.item_dnn = None if conventional else MatchDNN(user_dnn_hidden_units)
         self.sampler_layer = SampledSoftmaxLayer(num_sampled)
         self._step = 0
+        self.seed_dev = None
+
+    def enable_device_seed(self, device):
+        """The sampler's per-step seed (the step counter) in device memory, bumped by advance():
+        the candidate draw then changes on every replay of a captured step (core.StepGraph).
+        Same seeds, hence the same candidates, as the host-seeded path."""
+        if self.seed_dev is None:
+            self.seed_dev = torch.full((1,), self._step, dtype=torch.int64, device=device)
+
+    def advance(self):
+        self._step += 1
+        self.seed_dev.fill_(self._step)
 
     def call(self, inputs, sampled_values=None, **kwargs):
         from .layers.match import sampled_softmax_loss
         user_ids, item_ids = (_as_int_ids(t) for t in inputs[:2])
         user_out = self.user_dnn(self.user_tables.lookup(user_ids))             # (B, width)
-        self._step += 1
+        if self.seed_dev is None:
+            self._step += 1
         if self.conventional:
             loss = sampled_softmax_loss(self.item_table.weights[0], None, item_ids, user_out,
                                         self.num_sampled, self.item_num,
-                                        sampled_values=sampled_values, seed=self._step,
+                                        sampled_values=sampled_values,
+                                        seed=self._step if self.seed_dev is None else self.seed_dev,
                                         err=self.item_table.err, table=(self.item_table, 0))
             return loss.unsqueeze(1)
         item_out = self.item_dnn(self.item_table.lookup(item_ids.reshape(-1, 1)))
@@ -269,8 +283,9 @@ class Trainer:
     The lazily built layers are created by a no-grad eval forward on the first batch (BatchNorm
     moving statistics and the tables do not move)."""
 
-    def __init__(self, model: Layer, loss_fn, lr: float = 1e-3, embed_l2: float = 0.0):
-        from .core import DenseAdam
+    def __init__(self, model: Layer, loss_fn, lr: float = 1e-3, embed_l2: float = 0.0,
+                 cuda_graph: bool = False):
+        from .core import DenseAdam, StepGraph
         self._DenseAdam = DenseAdam
         self.model, self.loss_fn, self.lr = model, loss_fn, lr
         self.tables = [m for m in model.modules() if isinstance(m, EmbeddingTables)]
@@ -278,6 +293,10 @@ class Trainer:
             if ts.optimizer is None:
                 ts.set_optimizer(SparseOptimizer("adam", lr=lr, l2=embed_l2))
         self.dense_opt = None
+        # cuda_graph: replay the step from a CUDA graph (core.StepGraph) — for the launch-bound
+        # small models; per-step host values (the Adam step size, YoutubeDNN's sampler seed)
+        # move to device scalars refreshed before each replay
+        self.graph = StepGraph(self._body, self._advance) if cuda_graph else None
 
     def _setup(self, inputs):
         was = self.model.training
@@ -288,18 +307,38 @@ class Trainer:
         emb = {id(p) for ts in self.tables for p in ts.parameters()}
         params = [p for p in self.model.parameters() if id(p) not in emb and p.requires_grad]
         self.dense_opt = self._DenseAdam(params, lr=self.lr)
+        if self.graph is not None:
+            self.dense_opt.enable_device_lr()
+            for ts in self.tables:
+                if ts.optimizer is not None:
+                    ts.optimizer.enable_device_lr(self.dense_opt.flat.device)
+            if hasattr(self.model, "enable_device_seed"):       # per-step host values -> memory
+                self.model.enable_device_seed(self.dense_opt.flat.device)
 
-    def step(self, inputs, labels=None) -> torch.Tensor:
-        if self.dense_opt is None:
-            self._setup(inputs)
+    def _advance(self):
         seen = set()
         for ts in self.tables:          # one optimizer object may serve several table sets
             if ts.optimizer is not None and id(ts.optimizer) not in seen:
                 seen.add(id(ts.optimizer))
                 ts.begin_step()
+        self.dense_opt.advance()
+        if getattr(self.model, "seed_dev", None) is not None:
+            self.model.advance()
+
+    def _body(self, inputs, labels):
         out = self.model(inputs)
         loss = self.loss_fn(out, labels)
         self.dense_opt.zero_grad()
         loss.backward()
-        self.dense_opt.step()
+        self.dense_opt.apply()
+        for ts in self.tables:
+            ts.wait_pending()
         return loss.detach()
+
+    def step(self, inputs, labels=None) -> torch.Tensor:
+        if self.dense_opt is None:
+            self._setup(inputs)
+        if self.graph is not None:
+            return self.graph(inputs, labels)
+        self._advance()
+        return self._body(inputs, labels)

@@ -125,6 +125,7 @@ class RtfEmbedBwdAdamOp : public OpKernel {
     OP_REQUIRES_OK(c, c->GetAttr("epsilon", &opt_.eps));
     OP_REQUIRES_OK(c, c->GetAttr("l2", &opt_.l2));
     opt_.kind = RTF_OPT_ADAM;
+    opt_.lr_dev = nullptr;
   }
   void Compute(OpKernelContext* ctx) override {
     OpInputList tabs, ms, vs;
