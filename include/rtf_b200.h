@@ -337,6 +337,26 @@ int rtf_relu_bwd_colsum_workspace(int64_t B, int cols, size_t* bytes);
 int rtf_relu_bwd_colsum(const float* d_gy, const float* d_y, int64_t B, int cols, float* d_g,
                         float* d_colsum, void* d_ws, void* stream);
 
+/* ---- BatchNormalization of the DNN block (MLP either side of the path) -------
+ * replaces: tensorflow.keras.layers.BatchNormalization in training mode at the head of
+ *           ctr.layers.modules.DNN (src/ctr/layers/modules.py:129-135; Keras defaults App. A9)
+ *           and its gradient (FusedBatchNormV3 / FusedBatchNormGradV3).
+ * x (B,C) rows ldx floats apart.  fwd: batch mean / biased variance per column (one pass, sums
+ * shifted by row 0, chunk partials combined in double in chunk order — deterministic),
+ * y = (x-mean)*gamma/sqrt(var+eps)+beta, moving = moving*momentum + batch*(1-momentum).
+ * bwd: dbeta = sum dy, dgamma = invstd*sum dy(x-mean),
+ *      dx = (dy - dbeta/B - (x-mean)*invstd^2*sum dy(x-mean)/B)*gamma*invstd.
+ * NULL allowed: gamma, beta (scale/center off), y (statistics only), moving_*, dx, dgamma, dbeta. */
+int rtf_bn_workspace(int64_t B, int C, size_t* bytes);
+int rtf_bn_fwd(const float* d_x, int64_t ldx, int64_t B, int C, const float* d_gamma,
+               const float* d_beta, float eps, float momentum, float* d_y, int64_t ldy,
+               float* d_mean, float* d_invstd, float* d_moving_mean, float* d_moving_var,
+               void* d_ws, size_t ws_bytes, void* stream);
+int rtf_bn_bwd(const float* d_dy, int64_t lddy, const float* d_x, int64_t ldx, int64_t B, int C,
+               const float* d_mean, const float* d_invstd, const float* d_gamma, float* d_dx,
+               int64_t lddx, float* d_dgamma, float* d_dbeta, void* d_ws, size_t ws_bytes,
+               void* stream);
+
 /* ---- dense-layer GEMMs (MLP either side of the path) --------------------------
  * replaces: the MatMul (+BiasAdd+Relu) of tensorflow.keras.layers.Dense inside
  *           ctr.layers.modules.DNN (src/ctr/layers/modules.py:114-135) and its two gradient

@@ -62,6 +62,10 @@ SIGNATURES = {
                                _i64, _p, _i64, _p, _p, _int, C.c_uint64, _i64, _p],
     "rtf_colsum_workspace": [_i64, _int, C.POINTER(C.c_size_t)],
     "rtf_colsum": [_p, _i64, _p, _i64, _int, _p, _p, _p],
+    "rtf_bn_workspace": [_i64, _int, C.POINTER(C.c_size_t)],
+    "rtf_bn_fwd": [_p, _i64, _i64, _int, _p, _p, C.c_float, C.c_float, _p, _i64, _p, _p, _p, _p, _p,
+                   C.c_size_t, _p],
+    "rtf_bn_bwd": [_p, _i64, _p, _i64, _i64, _int, _p, _p, _p, _p, _i64, _p, _p, _p, C.c_size_t, _p],
     "rtf_relu_bwd_colsum_workspace": [_i64, _int, C.POINTER(C.c_size_t)],
     "rtf_relu_bwd_colsum": [_p, _p, _i64, _int, _p, _p, _p, _p],
     "rtf_autoint_layer_supported": [_int, _int, _int, _int],

@@ -323,6 +323,63 @@ class _DenseFn(torch.autograd.Function):
         return gx, gw, gb, None
 
 
+class _BatchNormTrainFn(torch.autograd.Function):
+    """Training-mode BatchNormalization through librtf_b200 (rtf_bn_fwd / rtf_bn_bwd): batch
+    statistics + normalisation + the Keras moving-average update in the forward, (dx, dgamma,
+    dbeta) in the backward; the column reductions are deterministic two-stage sums."""
+
+    @staticmethod
+    def forward(ctx, x2, gamma, beta, eps, momentum, moving_mean, moving_var):
+        import ctypes as C
+        from . import _lib as L
+        L.require_cuda(x2, "BatchNormalization(x)")
+        if x2.dtype != torch.float32:
+            raise TypeError("BatchNormalization: fp32 activations only")
+        if x2.stride(1) != 1:
+            x2 = x2.contiguous()
+        B, Cc = x2.shape
+        key = ("bn", B, Cc)
+        if key not in _GEMM_WS_BYTES:
+            nb = C.c_size_t(0)
+            L.check(L.lib().rtf_bn_workspace(B, Cc, C.byref(nb)), "rtf_bn_workspace")
+            _GEMM_WS_BYTES[key] = nb.value
+        ws = _scratch(_GEMM_WS_BYTES[key], x2.device)
+        y = torch.empty((B, Cc), dtype=torch.float32, device=x2.device)
+        stats = torch.empty((2, Cc), dtype=torch.float32, device=x2.device)
+        L.check(L.lib().rtf_bn_fwd(x2.data_ptr(), x2.stride(0), B, Cc,
+                                   None if gamma is None else gamma.data_ptr(),
+                                   None if beta is None else beta.data_ptr(), eps, momentum,
+                                   y.data_ptr(), y.stride(0), stats[0].data_ptr(), stats[1].data_ptr(),
+                                   None if moving_mean is None else moving_mean.data_ptr(),
+                                   None if moving_var is None else moving_var.data_ptr(),
+                                   ws.data_ptr(), ws.numel(), L.current_stream_ptr()), "rtf_bn_fwd")
+        ctx.save_for_backward(x2, stats, gamma)
+        ctx.has_beta = beta is not None
+        return y
+
+    @staticmethod
+    def backward(ctx, dy):
+        import ctypes as C
+        from . import _lib as L
+        x2, stats, gamma = ctx.saved_tensors
+        B, Cc = x2.shape
+        if dy.stride(1) != 1:
+            dy = dy.contiguous()
+        ws = _scratch(_GEMM_WS_BYTES[("bn", B, Cc)], x2.device)
+        dx = torch.empty_like(dy) if ctx.needs_input_grad[0] else None
+        dg = torch.empty(Cc, dtype=torch.float32, device=dy.device) if gamma is not None else None
+        db = torch.empty(Cc, dtype=torch.float32, device=dy.device) if ctx.has_beta else None
+        L.check(L.lib().rtf_bn_bwd(dy.data_ptr(), dy.stride(0), x2.data_ptr(), x2.stride(0), B, Cc,
+                                   stats[0].data_ptr(), stats[1].data_ptr(),
+                                   None if gamma is None else gamma.data_ptr(),
+                                   None if dx is None else dx.data_ptr(),
+                                   0 if dx is None else dx.stride(0),
+                                   None if dg is None else dg.data_ptr(),
+                                   None if db is None else db.data_ptr(),
+                                   ws.data_ptr(), ws.numel(), L.current_stream_ptr()), "rtf_bn_bwd")
+        return dx, dg, db, None, None, None, None
+
+
 class BatchNormalization(Layer):
     """Keras defaults (A9): momentum 0.99, eps 1e-3, batch statistics in training."""
 
@@ -342,11 +399,12 @@ class BatchNormalization(Layer):
     def call(self, x, **kwargs):
         shp = x.shape
         x2 = x.reshape(-1, shp[-1])
-        if self.training:
-            # Keras updates moving_variance with the BIASED batch variance (torch's running_var
-            # takes the unbiased one), so the moving statistics are kept here — from the batch
-            # statistics the normalisation kernel returns anyway (mean, 1/sqrt(var + eps)): no
-            # extra pass over the activations
+        if self.training and x2.is_cuda and x2.shape[0] > 0:
+            # batch statistics, normalisation and Keras' moving averages (BIASED batch variance;
+            # torch's running_var would take the unbiased one) in rtf_bn_fwd
+            y = _BatchNormTrainFn.apply(x2, self.gamma, self.beta, self.epsilon, self.momentum,
+                                        self.moving_mean, self.moving_variance)
+        elif self.training:       # CPU tensors: layer-building / checkpoint tests without a GPU
             y, mean, invstd = torch.native_batch_norm(x2, self.gamma, self.beta, None, None, True, 0.0,
                                                       self.epsilon)
             with torch.no_grad():

@@ -11,13 +11,18 @@ namespace rtf {
 
 constexpr int RB_ROWS = 128;
 
+// CTA = lx column lanes (float4 each) x 128/lx row lanes; a row lane owns RB_ROWS/(128/lx)
+// consecutive rows of the chunk and writes its own partial row, so narrow layers (N = 128: 32
+// column lanes) still fill the CTA
 __global__ void __launch_bounds__(128)
 relu_bwd_colsum_stage1(const float* __restrict__ gy, const float* __restrict__ y, long long B,
-                       int Ccols, float* __restrict__ g, float* __restrict__ partial) {
-  const int c4 = (blockIdx.x * blockDim.x + threadIdx.x) * 4;
+                       int Ccols, int lx, float* __restrict__ g, float* __restrict__ partial) {
+  const int tx = threadIdx.x % lx, ty = threadIdx.x / lx, ny = 128 / lx;
+  const int c4 = (blockIdx.x * lx + tx) * 4;
   if (c4 >= Ccols) return;
-  const long long b0 = (long long)blockIdx.y * RB_ROWS;
-  const long long b1 = min(b0 + RB_ROWS, B);
+  const int sub = RB_ROWS / ny;
+  const long long b0 = (long long)blockIdx.y * RB_ROWS + (long long)ty * sub;
+  const long long b1 = min(b0 + sub, B);
   float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
   for (long long b = b0; b < b1; ++b) {
     const float4 gv = *reinterpret_cast<const float4*>(gy + b * Ccols + c4);
@@ -32,7 +37,7 @@ relu_bwd_colsum_stage1(const float* __restrict__ gy, const float* __restrict__ y
     }
     acc = f4_add(acc, o);
   }
-  *reinterpret_cast<float4*>(partial + (long long)blockIdx.y * Ccols + c4) = acc;
+  *reinterpret_cast<float4*>(partial + ((long long)blockIdx.y * ny + ty) * Ccols + c4) = acc;
 }
 
 // 32 columns per CTA, 8 warps: warp g adds chunks g, g+8, g+16, ... (ascending), the 8 partial
@@ -70,9 +75,15 @@ relu_bwd_colsum_stage2(const float* __restrict__ partial, int nchunks, int Ccols
 
 using namespace rtf;
 
+static int relu_bwd_lx(int cols) {   // column lanes per CTA: 32, 64 or 128
+  const int v = cols / 4;
+  return v <= 32 ? 32 : (v <= 64 ? 64 : 128);
+}
+
 extern "C" int rtf_relu_bwd_colsum_workspace(int64_t B, int cols, size_t* bytes) {
   if (!bytes || B < 0 || cols <= 0) return RTF_E_ARG;
-  *bytes = (size_t)((B + RB_ROWS - 1) / RB_ROWS + 1) * (size_t)cols * 4;
+  const size_t ny = 128 / relu_bwd_lx(cols);
+  *bytes = (size_t)((B + RB_ROWS - 1) / RB_ROWS + 1) * ny * (size_t)cols * 4;
   return 0;
 }
 
@@ -88,9 +99,10 @@ extern "C" int rtf_relu_bwd_colsum(const float* d_gy, const float* d_y, int64_t 
       (uintptr_t)d_ws % 16)
     return RTF_E_ALIGN;
   const int nchunks = (int)((B + RB_ROWS - 1) / RB_ROWS);
-  dim3 g1((cols / 4 + 127) / 128, nchunks);
-  relu_bwd_colsum_stage1<<<g1, 128, 0, st>>>(d_gy, d_y, B, cols, d_g, (float*)d_ws);
-  relu_bwd_colsum_stage2<<<(cols + 31) / 32, 256, 0, st>>>((const float*)d_ws, nchunks, cols,
+  const int lx = relu_bwd_lx(cols), ny = 128 / lx;
+  dim3 g1((cols / 4 + lx - 1) / lx, nchunks);
+  relu_bwd_colsum_stage1<<<g1, 128, 0, st>>>(d_gy, d_y, B, cols, lx, d_g, (float*)d_ws);
+  relu_bwd_colsum_stage2<<<(cols + 31) / 32, 256, 0, st>>>((const float*)d_ws, nchunks * ny, cols,
                                                            d_colsum);
   RTF_CHECK_LAUNCH();
   return 0;

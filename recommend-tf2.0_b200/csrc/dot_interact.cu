@@ -14,6 +14,7 @@
 // dX = (S + S^T) X with lanes owning 4 embedding columns each.
 // Bound: HBM (ids + rows in, D+P floats out) with the fp32 FMA pipe close behind.
 #include <cstdlib>
+#include <type_traits>
 
 #include "rtf_common.cuh"
 
@@ -50,6 +51,8 @@ struct DotParams {
   long long sample0;           // bwd: global index of this rank's first sample
   int peer_G;
   int32_t* err;
+  int dbg;  // 0 in the product build.  With -DRTF_DOT_EXPERIMENTS, RTF_DOT_DBG sets bits that switch
+            // phases off to time the others: 1 = FMA loop, 2 = row gather, 4 = bwd S fill
 };
 
 __device__ __forceinline__ void peer_split(const DotParams& P, int f, long long id, int& g,
@@ -139,13 +142,13 @@ dot_fwd_kernel(const __grid_constant__ DotParams P, int warp_floats) {
   const long long stride = (long long)gridDim.x * nwarps;
   long long b = (long long)blockIdx.x * nwarps + warp;
   uint32_t parity = 0;
-  if (b < P.B) dot_issue_rows<IdT>(P, b, xt, RS, bar, lane);
+  if (b < P.B && !(P.dbg & 2)) dot_issue_rows<IdT>(P, b, xt, RS, bar, lane);
   const int nblk = nbr * (nbr + 1) / 2;
 
   for (; b < P.B; b += stride) {
-    mbar_wait(bar, parity);
+    if (!(P.dbg & 2)) mbar_wait(bar, parity);
     parity ^= 1;
-    for (int blk = lane; blk < nblk; blk += 32) {
+    for (int blk = lane; blk < ((P.dbg & 1) ? 0 : nblk); blk += 32) {
       int bi, bj;
       tri_block(blk, bi, bj);
       // block (bi,bj) covers rows {bi + r*nbr} x {bj + c*nbr}
@@ -200,7 +203,138 @@ dot_fwd_kernel(const __grid_constant__ DotParams P, int warp_floats) {
       }
     }
     __syncwarp();  // every lane is done reading xt/zst before the next sample overwrites them
-    if (b + stride < P.B) dot_issue_rows<IdT>(P, b + stride, xt, RS, bar, lane);
+    if (b + stride < P.B && !(P.dbg & 2)) dot_issue_rows<IdT>(P, b + stride, xt, RS, bar, lane);
+  }
+}
+
+// Forward, 7x7 register blocks.  The 4x4 kernel above is bound by shared-memory wavefronts (ncu,
+// profiles/r2_ncu_full_summary.txt: 71 M wavefronts; with the row gather switched off it still
+// takes 0.30 of its 0.37 ms, with the Gram loop switched off 0.12): a lane loads 8 float4 per 32
+// packed FMAs, and a shared load costs wavefronts by the bytes each lane receives, broadcast or
+// not.  Here a lane owns a 7x7 block of the Gram matrix (rows {bi + r*nbr} x {bj + c*nbr}: 10
+// blocks of the lower triangle for 22..28 rows) and the lanes left over split the embedding
+// dimension: lane = (block, d-group), d-group g takes the float2 columns g, g + G, ... (G = 32 /
+// blocks = 3).  14 float2 loads feed 49 packed FMAs: 0.57 wavefronts per FMA2 instead of 1.0.
+// The G partial blocks are added in group order with two shuffles (deterministic) and group 0
+// stores its block into a square Z tile with immediate offsets — no per-element branches; the
+// packed lower triangle is read back through a (p -> position) table.  The next sample's row
+// gather is issued as soon as the Gram loop has read the rows, under the reduction and stores.
+// D and the block-row count are template parameters so that the 14 shared-memory addresses of an
+// iteration are immediates off two base registers (runtime strides cost 14 address registers and
+// made ptxas reload q[c] into one register: 0.70 ms).  Bank map: word = row*(D+4) + 2e, the 16
+// lanes of a half-warp read (2 row + e) mod 16 distinct or identical addresses — conflict-free.
+template <typename IdT, int D, int nbr>
+__global__ void __launch_bounds__(384, 1)
+dot_fwd7_kernel(const __grid_constant__ DotParams P, int warp_floats) {
+  extern __shared__ __align__(16) float smem[];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
+  const int F1 = P.F1;
+  constexpr int F1p = nbr * 7;
+  constexpr int RS = D + ((D % 8 == 0) ? 4 : 8);
+  constexpr int ZS = F1p + 1;
+  const int npairs = F1 * (F1 - 1) / 2;
+  constexpr int nblk = nbr * (nbr + 1) / 2;
+  constexpr int ngrp = 32 / nblk;
+  const int blk = lane % nblk, grp = lane / nblk;    // grp >= ngrp: spare lane
+  // CTA-shared pair table, then per-warp regions
+  unsigned short* pair_ij = reinterpret_cast<unsigned short*>(smem);
+  const int pair_floats = ((npairs + 1) / 2 + 3) & ~3;
+  float* xt = smem + pair_floats + (size_t)warp * warp_floats;   // [F1p][RS]
+  float* Z = xt + F1p * RS;                                      // [F1p][ZS]
+  uint64_t* bar = reinterpret_cast<uint64_t*>(Z + ((F1p * ZS + 3) & ~3));
+  int bi, bj;
+  tri_block(blk, bi, bj);
+
+  for (int p = threadIdx.x; p < npairs; p += blockDim.x) {
+    int i = (int)((1.f + sqrtf(1.f + 8.f * p)) * 0.5f);
+    while (i * (i - 1) / 2 > p) --i;
+    while ((i + 1) * i / 2 <= p) ++i;
+    // pair (i, j), i > j, is computed by block (max, min) of (i % nbr, j % nbr) and lands at
+    // Z[i][j] when i's block row is the larger one, else at Z[j][i]
+    const int j = p - i * (i - 1) / 2;
+    pair_ij[p] = (unsigned short)((i % nbr >= j % nbr) ? i * ZS + j : j * ZS + i);
+  }
+  if (lane == 0) {
+    mbar_init(bar, 1);
+    mbar_fence_init();
+  }
+  for (int i = F1 * RS + lane; i < F1p * RS; i += 32) xt[i] = 0.f;  // pad rows stay zero
+  __syncthreads();
+
+  const long long stride = (long long)gridDim.x * nwarps;
+  long long b = (long long)blockIdx.x * nwarps + warp;
+  uint32_t parity = 0;
+  if (b < P.B && !(P.dbg & 2)) dot_issue_rows<IdT>(P, b, xt, RS, bar, lane);
+  constexpr int rstep = nbr * RS;
+  constexpr int nd2 = D >> 1;
+  const float* pa = xt + bi * RS;
+  const float* pb = xt + bj * RS;
+  float* zd = Z + bi * ZS + bj;      // Z[i][j]
+
+  for (; b < P.B; b += stride) {
+    if (!(P.dbg & 2)) mbar_wait(bar, parity);
+    parity ^= 1;
+    float2 acc[7][7];
+#pragma unroll
+    for (int r = 0; r < 7; ++r)
+#pragma unroll
+      for (int c = 0; c < 7; ++c) acc[r][c] = make_float2(0.f, 0.f);
+    if (grp < ngrp && !(P.dbg & 1)) {
+#pragma unroll 1
+      for (int e = grp; e < nd2; e += ngrp) {
+        float2 a[7], q[7];
+#pragma unroll
+        for (int r = 0; r < 7; ++r) {
+          a[r] = *reinterpret_cast<const float2*>(pa + r * rstep + 2 * e);
+          q[r] = *reinterpret_cast<const float2*>(pb + r * rstep + 2 * e);
+        }
+#pragma unroll
+        for (int r = 0; r < 7; ++r)
+#pragma unroll
+          for (int c = 0; c < 7; ++c) acc[r][c] = __ffma2_rn(a[r], q[c], acc[r][c]);
+      }
+    }
+    // row 0 (passed through) and the optional row copy are the last readers of xt: take them
+    // now, so the next sample's gather runs under the reduction / store phase below
+    float x0[(D + 31) / 32];
+#pragma unroll
+    for (int k = 0; k < (D + 31) / 32; ++k) x0[k] = lane + 32 * k < D ? xt[lane + 32 * k] : 0.f;
+    if (P.xsave) {
+      float* xs = P.xsave + b * P.xsave_sb;
+      constexpr int nv = D >> 2;
+      for (int e = lane; e < (F1 - 1) * nv; e += 32) {
+        const int r = e / nv, c = e - r * nv;
+        *reinterpret_cast<float4*>(xs + r * D + 4 * c) =
+            *reinterpret_cast<const float4*>(xt + (r + 1) * RS + 4 * c);
+      }
+    }
+    __syncwarp();  // every lane is done reading xt
+    if (b + stride < P.B && !(P.dbg & 2)) dot_issue_rows<IdT>(P, b + stride, xt, RS, bar, lane);
+    // d-group partials -> group 0, added in group order
+    float z[7][7];
+#pragma unroll
+    for (int r = 0; r < 7; ++r)
+#pragma unroll
+      for (int c = 0; c < 7; ++c) {
+        const float part = acc[r][c].x + acc[r][c].y;
+        z[r][c] = part;
+#pragma unroll
+        for (int g = 1; g < ngrp; ++g) z[r][c] += __shfl_down_sync(0xffffffffu, part, g * nblk);
+      }
+    if (grp == 0) {     // Z[i][j], i = bi + r nbr, j = bj + c nbr (either triangle; see pair_ij)
+#pragma unroll
+      for (int r = 0; r < 7; ++r)
+#pragma unroll
+        for (int c = 0; c < 7; ++c) zd[r * (nbr * ZS) + c * nbr] = z[r][c];
+    }
+    __syncwarp();
+    float* o = P.out + b * P.out_sb;
+#pragma unroll
+    for (int k = 0; k < (D + 31) / 32; ++k)
+      if (lane + 32 * k < D) o[lane + 32 * k] = x0[k];
+    for (int p = lane; p < npairs; p += 32) o[D + p] = Z[pair_ij[p]];
+    for (int p = D + npairs + lane; p < P.out_cols; p += 32) o[p] = 0.f;
+    __syncwarp();  // every lane is done reading Z before the next sample overwrites it
   }
 }
 
@@ -342,6 +476,8 @@ dot_bwd_kernel(const __grid_constant__ DotParams P, int warp_floats) {
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
   const int F1 = P.F1, D = P.D;
   const int F1p = (F1 + 7) & ~7;  // i-tiles of 8 rows
+  const int SS = F1p + 4;         // S row stride: the mirrored writes S[j][i] of consecutive j would
+                                  // all hit one bank with a stride of 32
   const int RS = dot_row_stride(D);
   const int npairs = F1 * (F1 - 1) / 2;
   // CTA-shared pair table, then per-warp regions
@@ -349,8 +485,8 @@ dot_bwd_kernel(const __grid_constant__ DotParams P, int warp_floats) {
   const int pair_floats = ((npairs + 1) / 2 + 3) & ~3;
   float* wbase = smem + pair_floats + (size_t)warp * warp_floats;
   float* xt = wbase;                // [F1][RS]
-  float* S = xt + F1 * RS;          // [F1p][F1p]
-  uint64_t* bar = reinterpret_cast<uint64_t*>(S + F1p * F1p);
+  float* S = xt + F1 * RS;          // [F1][SS]
+  uint64_t* bar = reinterpret_cast<uint64_t*>(S + F1 * SS);
   long long* ids_w = reinterpret_cast<long long*>(bar + 2);  // [64] ids of this sample (peer bwd)
 
   for (int p = threadIdx.x; p < npairs; p += blockDim.x) {
@@ -363,13 +499,30 @@ dot_bwd_kernel(const __grid_constant__ DotParams P, int warp_floats) {
     mbar_init(bar, 1);
     mbar_fence_init();
   }
-  for (int i = lane; i < F1p * F1p; i += 32) S[i] = 0.f;  // diagonal and padding stay zero
+  for (int i = lane; i < F1 * SS; i += 32) S[i] = 0.f;  // diagonal and padding stay zero
   __syncthreads();
 
   const long long stride = (long long)gridDim.x * nwarps;
   long long b = (long long)blockIdx.x * nwarps + warp;
   uint32_t parity = 0;
-  if (b < P.B) dot_issue_rows<IdT>(P, b, xt, RS, bar, lane);
+  if (b < P.B && !(P.dbg & 2)) dot_issue_rows<IdT>(P, b, xt, RS, bar, lane);
+  // the incoming gradient of the NEXT sample is fetched into registers while this one is being
+  // processed (its HBM latency was a serial 0.07 ms in front of every sample's S fill)
+  constexpr int PF = 12;                     // covers F1 <= 28; longer tails are loaded in place
+  float gpre[PF];
+  float4 g0pre = make_float4(0.f, 0.f, 0.f, 0.f);
+  const bool g_vec = (P.gout_sb & 3) == 0 && (reinterpret_cast<uintptr_t>(P.gout) & 15) == 0;
+  auto prefetch = [&](long long bb) {
+    const float* gg = P.gout + bb * P.gout_sb;
+#pragma unroll
+    for (int q = 0; q < PF; ++q) gpre[q] = lane + 32 * q < npairs ? __ldg(gg + D + lane + 32 * q) : 0.f;
+    if (lane * 4 < D) {
+      if (g_vec) g0pre = __ldg(reinterpret_cast<const float4*>(gg + lane * 4));
+      else g0pre = make_float4(__ldg(gg + lane * 4), __ldg(gg + lane * 4 + 1), __ldg(gg + lane * 4 + 2),
+                               __ldg(gg + lane * 4 + 3));
+    }
+  };
+  if (b < P.B) prefetch(b);
 
   for (; b < P.B; b += stride) {
     const float* g = P.gout + b * P.gout_sb;
@@ -378,76 +531,101 @@ dot_bwd_kernel(const __grid_constant__ DotParams P, int warp_floats) {
         long long id = (long long)__ldg((const IdT*)P.ids + b * P.ids_sb + (long long)f * P.ids_sf);
         ids_w[f] = (id < 0 || id >= P.rows[f]) ? -1 : id;
       }
-    for (int p = lane; p < npairs; p += 32) {
-      const float v = __ldg(g + D + p);
-      const int ij = pair_ij[p];
-      const int i = ij >> 8, j = ij & 255;
-      S[i * F1p + j] = v;
-      S[j * F1p + i] = v;
+    if (!(P.dbg & 4)) {
+#pragma unroll
+      for (int q = 0; q < PF; ++q) {
+        const int p = lane + 32 * q;
+        if (p < npairs) {
+          const int ij = pair_ij[p];
+          const int i = ij >> 8, j = ij & 255;
+          S[i * SS + j] = gpre[q];
+          S[j * SS + i] = gpre[q];
+        }
+      }
+      for (int p = lane + 32 * PF; p < npairs; p += 32) {
+        const float v = __ldg(g + D + p);
+        const int ij = pair_ij[p];
+        const int i = ij >> 8, j = ij & 255;
+        S[i * SS + j] = v;
+        S[j * SS + i] = v;
+      }
     }
+    const float4 g0 = g0pre;
+    if (b + stride < P.B) prefetch(b + stride);
     __syncwarp();
-    mbar_wait(bar, parity);
+    if (!(P.dbg & 2)) mbar_wait(bar, parity);
     parity ^= 1;
-    for (int d0 = lane * 4; d0 < D; d0 += 128) {
-      for (int i0 = 0; i0 < F1; i0 += 8) {
-        // packed fp32x2 FMAs (sm_100 FFMA2), pairing ROWS: acc2[rp][c] = {dX[i0+2rp][d0+c],
-        // dX[i0+2rp+1][d0+c]}; the S pairs come straight out of the 128-bit loads and only the 4
-        // x values are duplicated in registers (a duplicated {s,s} tile in shared memory was
-        // measured slower: two warps of occupancy and twice the shared loads)
-        float2 acc2[4][4];
+    // one i-tile of 2*RPN rows (RPN = 4 except for the last tile, which only computes the row
+    // pairs that exist: 27 rows = 8 + 8 + 8 + 4, not 32).
+    // packed fp32x2 FMAs (sm_100 FFMA2), pairing ROWS: acc2[rp][c] = {dX[i0+2rp][d0+c],
+    // dX[i0+2rp+1][d0+c]}; the S pairs come straight out of the 128-bit loads and only the 4
+    // x values are duplicated in registers (a duplicated {s,s} tile in shared memory was
+    // measured slower: two warps of occupancy and twice the shared loads)
+    auto tile = [&](auto rpn_tag, int i0, int d0) {
+      constexpr int RPN = decltype(rpn_tag)::value;
+      float2 acc2[RPN][4];
 #pragma unroll
-        for (int rp = 0; rp < 4; ++rp)
+      for (int rp = 0; rp < RPN; ++rp)
 #pragma unroll
-          for (int c = 0; c < 4; ++c) acc2[rp][c] = make_float2(0.f, 0.f);
+        for (int c = 0; c < 4; ++c) acc2[rp][c] = make_float2(0.f, 0.f);
 #pragma unroll 3
-        for (int j = 0; j < F1; ++j) {
-          const float4 xj = *reinterpret_cast<const float4*>(xt + j * RS + d0);
-          const float4 s0 = *reinterpret_cast<const float4*>(S + j * F1p + i0);
-          const float4 s1 = *reinterpret_cast<const float4*>(S + j * F1p + i0 + 4);
-          const float2 sp[4] = {make_float2(s0.x, s0.y), make_float2(s0.z, s0.w),
-                                make_float2(s1.x, s1.y), make_float2(s1.z, s1.w)};
-          const float2 xx[4] = {make_float2(xj.x, xj.x), make_float2(xj.y, xj.y),
-                                make_float2(xj.z, xj.z), make_float2(xj.w, xj.w)};
+      for (int j = 0; j < ((P.dbg & 1) ? 0 : F1); ++j) {
+        const float4 xj = *reinterpret_cast<const float4*>(xt + j * RS + d0);
+        const float4 s0 = *reinterpret_cast<const float4*>(S + j * SS + i0);
+        float4 s1 = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (RPN > 2) s1 = *reinterpret_cast<const float4*>(S + j * SS + i0 + 4);
+        const float2 sp[4] = {make_float2(s0.x, s0.y), make_float2(s0.z, s0.w),
+                              make_float2(s1.x, s1.y), make_float2(s1.z, s1.w)};
+        const float2 xx[4] = {make_float2(xj.x, xj.x), make_float2(xj.y, xj.y),
+                              make_float2(xj.z, xj.z), make_float2(xj.w, xj.w)};
 #pragma unroll
-          for (int rp = 0; rp < 4; ++rp)
+        for (int rp = 0; rp < RPN; ++rp)
 #pragma unroll
-            for (int c = 0; c < 4; ++c) acc2[rp][c] = __ffma2_rn(sp[rp], xx[c], acc2[rp][c]);
-        }
-        float4 acc[8];
+          for (int c = 0; c < 4; ++c) acc2[rp][c] = __ffma2_rn(sp[rp], xx[c], acc2[rp][c]);
+      }
 #pragma unroll
-        for (int rp = 0; rp < 4; ++rp) {
-          acc[2 * rp] = make_float4(acc2[rp][0].x, acc2[rp][1].x, acc2[rp][2].x, acc2[rp][3].x);
-          acc[2 * rp + 1] = make_float4(acc2[rp][0].y, acc2[rp][1].y, acc2[rp][2].y, acc2[rp][3].y);
-        }
-#pragma unroll
-        for (int r = 0; r < 8; ++r) {
-          const int i = i0 + r;
-          if (i < F1) {
-            float4 v = acc[r];
-            float* dst;
-            if (P.peer_gptr && i > 0) {  // straight into the owner's gradient buffer over NVLink
-              const long long id = (long long)ids_w[i - 1];
-              int gq = 0;
-              long long row;
-              if (id >= 0) peer_split(P, i - 1, id, gq, row);
-              const int e = (i - 1) * P.peer_G + gq;
-              dst = reinterpret_cast<float*>(P.peer_gptr[e]) + (P.sample0 + b) * P.peer_gstr[e] + d0;
-            } else {
-              dst = P.gbase[i] + b * P.gstride[i] + d0;
-            }
-            if (i == 0) {  // out[:, :D] is X[0] itself
+      for (int r = 0; r < 2 * RPN; ++r) {
+        const int i = i0 + r;
+        if (i < F1) {
+          const int rp = r >> 1;
+          float4 v = (r & 1) ? make_float4(acc2[rp][0].y, acc2[rp][1].y, acc2[rp][2].y, acc2[rp][3].y)
+                             : make_float4(acc2[rp][0].x, acc2[rp][1].x, acc2[rp][2].x, acc2[rp][3].x);
+          float* dst;
+          if (P.peer_gptr && i > 0) {  // straight into the owner's gradient buffer over NVLink
+            const long long id = (long long)ids_w[i - 1];
+            int gq = 0;
+            long long row;
+            if (id >= 0) peer_split(P, i - 1, id, gq, row);
+            const int e = (i - 1) * P.peer_G + gq;
+            dst = reinterpret_cast<float*>(P.peer_gptr[e]) + (P.sample0 + b) * P.peer_gstr[e] + d0;
+          } else {
+            dst = P.gbase[i] + b * P.gstride[i] + d0;
+          }
+          if (i == 0) {  // out[:, :D] is X[0] itself
+            if (d0 == lane * 4) {
+              v.x += g0.x; v.y += g0.y; v.z += g0.z; v.w += g0.w;
+            } else {       // D > 128: later column passes
               v.x += __ldg(g + d0);
               v.y += __ldg(g + d0 + 1);
               v.z += __ldg(g + d0 + 2);
               v.w += __ldg(g + d0 + 3);
             }
-            *reinterpret_cast<float4*>(dst) = v;
           }
+          *reinterpret_cast<float4*>(dst) = v;
         }
+      }
+    };
+    for (int d0 = lane * 4; d0 < D; d0 += 128) {
+      for (int i0 = 0; i0 < F1; i0 += 8) {
+        const int left = F1 - i0;
+        if (left > 6) tile(std::integral_constant<int, 4>{}, i0, d0);
+        else if (left > 4) tile(std::integral_constant<int, 3>{}, i0, d0);
+        else if (left > 2) tile(std::integral_constant<int, 2>{}, i0, d0);
+        else tile(std::integral_constant<int, 1>{}, i0, d0);
       }
     }
     __syncwarp();
-    if (b + stride < P.B) dot_issue_rows<IdT>(P, b + stride, xt, RS, bar, lane);
+    if (b + stride < P.B && !(P.dbg & 2)) dot_issue_rows<IdT>(P, b + stride, xt, RS, bar, lane);
   }
 }
 
@@ -695,12 +873,12 @@ static int dot_check_common(long long B, int F1, int D) {
 
 template <typename Kern>
 static int dot_launch(Kern kern, const DotParams& P, int warp_floats, int cta_floats,
-                      cudaStream_t st) {
+                      cudaStream_t st, int max_warps = 16) {
   const size_t max_smem = 227 * 1024;
   const size_t per_warp = (size_t)warp_floats * 4;
   int nwarps = (int)((max_smem - (size_t)cta_floats * 4) / per_warp);
   if (nwarps < 1) return RTF_E_RANGE;
-  if (nwarps > 16) nwarps = 16;
+  if (nwarps > max_warps) nwarps = max_warps;
   const size_t smem = (size_t)cta_floats * 4 + per_warp * nwarps;
   cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   if (e != cudaSuccess) return (int)e;
@@ -739,6 +917,10 @@ static bool dot_use_fwd_v2(int D) {
 #endif  // RTF_DOT_EXPERIMENTS
 
 static int dot_fwd_impl(DotParams& P, int ids_i64, cudaStream_t st) {
+#ifdef RTF_DOT_EXPERIMENTS   // phase-isolation switches (wrong results by design): experiments only
+  static const int dbg = getenv("RTF_DOT_DBG") ? atoi(getenv("RTF_DOT_DBG")) : 0;
+  P.dbg = dbg;
+#endif
   const int F1p = (P.F1 + 3) & ~3, RS = dot_row_stride(P.D);
   const int npairs = P.F1 * (P.F1 - 1) / 2;
 #ifdef RTF_DOT_EXPERIMENTS
@@ -754,11 +936,27 @@ static int dot_fwd_impl(DotParams& P, int ids_i64, cudaStream_t st) {
                    : dot_launch(dot_fwd_mma_kernel<int32_t>, P, wf, 0, st);
   }
 #endif
+  {   // 7x7 register blocks (instantiated for the shape the bench and the reference's Criteo
+      // DLRM use; every other shape takes the generic 4x4 kernel)
+    const int nbr7 = (P.F1 + 6) / 7;
+    static const int variant = getenv("RTF_DOT_FWD") ? atoi(getenv("RTF_DOT_FWD")) : 7;
+    if (variant == 7 && nbr7 == 4 && P.D == 128) {     // the Criteo shape: 22..28 rows of 128
+      const int wf = 28 * RS + ((28 * 29 + 3) & ~3) + 4;    // rows, Z tile, mbarrier
+      const int cf = ((npairs + 1) / 2 + 3) & ~3;           // pair table
+      // 12 warps (154 registers each); measured 12 / 11 / 10 / 8 warps: 0.305 / 0.327 / 0.374 / 0.396 ms
+      return ids_i64 ? dot_launch(dot_fwd7_kernel<int64_t, 128, 4>, P, wf, cf, st, 12)
+                     : dot_launch(dot_fwd7_kernel<int32_t, 128, 4>, P, wf, cf, st, 12);
+    }
+  }
   const int warp_floats = F1p * RS + ((npairs + 3) & ~3) + 4;  // + mbarrier (8 B, 16-B slot)
   return ids_i64 ? dot_launch(dot_fwd_kernel<int64_t>, P, warp_floats, 0, st)
                  : dot_launch(dot_fwd_kernel<int32_t>, P, warp_floats, 0, st);
 }
 static int dot_bwd_impl(DotParams& P, int ids_i64, cudaStream_t st) {
+#ifdef RTF_DOT_EXPERIMENTS
+  static const int dbg = getenv("RTF_DOT_DBG") ? atoi(getenv("RTF_DOT_DBG")) : 0;
+  P.dbg = dbg;
+#endif
   const int F1p = (P.F1 + 7) & ~7, RS = dot_row_stride(P.D);
   const int npairs = P.F1 * (P.F1 - 1) / 2;
 #ifdef RTF_DOT_EXPERIMENTS
@@ -769,7 +967,7 @@ static int dot_bwd_impl(DotParams& P, int ids_i64, cudaStream_t st) {
                    : dot_launch(dot_bwd_mma_kernel<int32_t>, P, wf, cf, st);
   }
 #endif
-  const int warp_floats = P.F1 * RS + F1p * F1p + 4 + 128;  // + mbarrier slot + 64 ids
+  const int warp_floats = P.F1 * RS + P.F1 * (F1p + 4) + 4 + 128;  // + mbarrier slot + 64 ids
   const int cta_floats = ((npairs + 1) / 2 + 3) & ~3;
   return ids_i64 ? dot_launch(dot_bwd_kernel<int64_t>, P, warp_floats, cta_floats, st)
                  : dot_launch(dot_bwd_kernel<int32_t>, P, warp_floats, cta_floats, st);
