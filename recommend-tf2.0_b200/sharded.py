@@ -305,6 +305,7 @@ class ShardedDLRM(Layer):
         dense_fea = self.bot_dnn(dense_inputs)            # overlaps the all-to-all
         work.wait()
         x = _ShardedInteractFn.apply(self, dense_fea, recv, self.pad_to)
+        x = _TopGradsReady.apply(x, self)
         return torch.sigmoid(self.final_dense(self.top_dnn(x)))
 
     # ---- exchange over NVLink peer memory (torch symmetric memory for the address exchange)
@@ -338,6 +339,7 @@ class ShardedDLRM(Layer):
         self._out_hdl.barrier(channel=0)      # every owner's rows are in place (stream-ordered)
         x = _PeerInteractFn.apply(self, dense_fea, self.pad_to)
         self._out_inflight = True
+        x = _TopGradsReady.apply(x, self)
         return torch.sigmoid(self.final_dense(self.top_dnn(x)))
 
     def finish_backward(self):
@@ -365,6 +367,25 @@ class ShardedDLRM(Layer):
         return [p for p in self.parameters() if id(p) not in emb]
 
 
+class _TopGradsReady(torch.autograd.Function):
+    """Identity on the interaction output.  Its backward runs when every gradient of the top MLP
+    exists (autograd accumulates a layer's weight gradients before it walks further down), so the
+    trainer's hook starts their all-reduce there — under K4's backward, the reverse exchange and
+    the bottom MLP's backward instead of after them."""
+
+    @staticmethod
+    def forward(ctx, x, owner):
+        ctx.owner = owner
+        return x.view_as(x)
+
+    @staticmethod
+    def backward(ctx, g):
+        cb = getattr(ctx.owner, "_top_grads_hook", None)
+        if cb is not None:
+            cb()
+        return g, None
+
+
 class ShardedDLRMTrainer:
     """Per-rank step: local loss / world (so that summed gradients equal the global-batch mean,
     as MirroredStrategy scales them, App. A18), reverse exchange + K2 on owners, one flat
@@ -390,6 +411,12 @@ class ShardedDLRMTrainer:
         for t in params + bufs:                            # same start on every rank
             dist.broadcast(t.data, 0)
         self.dense_opt = DenseAdam(params, lr=self.lr)
+        # flat-buffer offset where the top MLP's (and the output layer's) gradients start: they are
+        # all-reduced as soon as they exist (_TopGradsReady), the bottom MLP's after the backward
+        top = {id(p) for p in list(m.top_dnn.parameters()) + list(m.final_dense.parameters())}
+        first = [i for i, p in enumerate(self.dense_opt.params) if id(p) in top]
+        tail = all(id(p) in top for p in self.dense_opt.params[first[0]:]) if first else False
+        self._top_off = self.dense_opt.offsets[first[0]] if tail and first[0] > 0 else None
         if hasattr(m, "async_update"):
             m.async_update = True       # step() always ends with finish_backward()
 
@@ -404,16 +431,25 @@ class ShardedDLRMTrainer:
         pred = m([dense, sparse])
         loss = binary_crossentropy(labels, pred)
         self.dense_opt.zero_grad()
-        (loss / m.world).backward()
-        # one all-reduce of the persistent flat MLP-gradient buffer (no concat / copy-back),
-        # asynchronous so that it overlaps the reverse exchange barrier + K2 on the embedding
-        # shards (finish_backward)
-        work = dist.all_reduce(self.dense_opt.flat_grad, async_op=True)
+        # all-reduce of the persistent flat MLP-gradient buffer (no concat / copy-back) in two
+        # pieces: the top MLP's slice from inside the backward, the moment it is complete, the
+        # rest after it; both asynchronous, overlapping K4's backward, the bottom MLP's backward,
+        # the reverse exchange barrier and K2 on the embedding shards (finish_backward)
+        fg, works = self.dense_opt.flat_grad, []
+        if self._top_off is not None:
+            m._top_grads_hook = lambda: works.append(dist.all_reduce(fg[self._top_off:], async_op=True))
+        try:
+            (loss / m.world).backward()
+        finally:
+            m._top_grads_hook = None
+        work = dist.all_reduce(fg[:self._top_off] if works else fg, async_op=True)
         pipelined = next_sparse is not None and hasattr(m, "prefetch") and m.async_update
         if pipelined:
             m.prefetch(next_sparse)
         elif not getattr(m, "async_update", False):
             m.finish_backward()
+        for w in works:
+            w.wait()
         work.wait()
         self.dense_opt.step()
         if not pipelined:
@@ -855,6 +891,7 @@ class PeerShardedDLRM(Layer):
             # every rank's row updates of the previous step are complete before anyone pulls
             self._tab_hdl.barrier(channel=0)
         x = _PeerDotFn.apply(self, sparse_inputs, dense_fea, self.pad_to)
+        x = _TopGradsReady.apply(x, self)
         return torch.sigmoid(self.final_dense(self.top_dnn(x)))
 
     def _launch_update(self):
