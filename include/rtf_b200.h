@@ -86,7 +86,8 @@ int rtf_embed_fwd(const float* const* tables, const int64_t* rows, const int32_t
  *           model.compile(optimizer=Adam) src/ctr/fm/train.py:49-50
  * sort (table,id) keys (stable LSD radix, payload = lookup position), find the
  * segments, sum each segment's gradient rows in ascending lookup position
- * (chunks of RTF_SEG_CHUNK rows, chunk partials combined in order), then apply
+ * (chunks of RTF_SEG_CHUNK rows; the chunk partials of every RTF_SEG_GROUP consecutive chunks
+ * are added in chunk order, the group sums in group order), then apply
  * `opt` to the touched rows.  Lookup position p = (b*L + l)*n_fields + f.
  * field_table[f] (HOST) maps a field to one of n_tables distinct tables;
  * weights/state1/state2/rows/dims are HOST arrays of n_tables entries
@@ -95,6 +96,7 @@ int rtf_embed_fwd(const float* const* tables, const int64_t* rows, const int32_t
  * d_uniq_key[n] (table*2^row_bits + row, ascending), d_uniq_grad[n, dim_max]
  * (the summed rows), d_num_uniq[1], and *row_bits_out (HOST). */
 #define RTF_SEG_CHUNK 64
+#define RTF_SEG_GROUP 64
 int rtf_embed_bwd_workspace(int64_t n_lookups, int dim_max, size_t* bytes);
 int rtf_embed_bwd(float* const* weights, float* const* state1, float* const* state2,
                   const int64_t* rows, const int32_t* dims, int n_tables,

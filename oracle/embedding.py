@@ -9,6 +9,7 @@ from __future__ import annotations
 import numpy as np
 
 SEG_CHUNK = 64  # == RTF_SEG_CHUNK in include/rtf_b200.h
+SEG_GROUP = 64  # == RTF_SEG_GROUP: chunk partials are added per group of 64 chunks, then the groups
 
 
 def embed_lookup_concat(tables, ids_bfl, pool=None):
@@ -64,7 +65,8 @@ def embed_grad_unique(ids_bfl, field_table, rows, dims, grad, pool=None, chunk=S
     """The IndexedSlices -> UnsortedSegmentSum reduction implied by the backward of the
     gathers, with the order fixed: for every touched (table,row), gradient
     rows are added in ascending lookup position; segments longer than `chunk` are summed as
-    chunk partials combined in chunk order.
+    chunk partials; the partials of every `SEG_GROUP` consecutive chunks are added in chunk order,
+    the group sums in group order (one group = the plain chunk-order sum).
       grad: (B, L, sumD) for pool None, (B, sumD) for pooled lookups.
     returns (keys ascending int64, (n_unique, dim_max) fp32 sums, row_bits)."""
     ids = np.asarray(ids_bfl)
@@ -107,9 +109,15 @@ def embed_grad_unique(ids_bfl, field_table, rows, dims, grad, pool=None, chunk=S
     cuid = np.cumsum(chunk_head) - 1                       # unique (segment, chunk) id, ascending
     partial = np.zeros((cuid[-1] + 1, dim_max), np.float32)
     np.add.at(partial, cuid, g[order])                     # sequential fp32 adds, ascending p
+    # group sums: partials in chunk order inside each group of SEG_GROUP chunks ...
+    pseg, pch = seg[chunk_head], ch[chunk_head]
+    group_head = (pch % SEG_GROUP) == 0
+    guid = np.cumsum(group_head) - 1
+    gsum = np.zeros((guid[-1] + 1, dim_max), np.float32)
+    np.add.at(gsum, guid, partial)
+    # ... then the group sums in group order
     total = np.zeros((seg[-1] + 1, dim_max), np.float32)
-    np.add.at(total, seg[chunk_head], partial)             # partials in chunk order
-    del ch
+    np.add.at(total, pseg[group_head], gsum)
     return sk[head], total, row_bits
 
 

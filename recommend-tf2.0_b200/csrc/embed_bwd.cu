@@ -203,7 +203,8 @@ struct OutSegments {
 //   short segment (len <= RTF_SEG_CHUNK): {key, start, len, vals[start]}      at items[cap_chunk + j]
 //   chunk c of a long segment:            {key, start + c*CH, len_c, slot0}   at items[slot0 + c]
 // slot0 = first chunk slot of the segment; long_seg[slot0] = {segment index, #chunks} and
-// arrive[slot0] is the segment's arrival counter.
+// arrive[slot0] is the segment's arrival counter (arrive[slot0 + 1 + g]: chunk group g's, for
+// segments of more than RTF_SEG_GROUP chunks).
 struct InSegKinds {  // low 32 bits: 1 for a short segment; high 32 bits: #chunks of a long one
   const uint32_t* seg_start;
   const int32_t* counters;
@@ -236,9 +237,9 @@ struct OutItems {
     } else {
       const uint32_t nch = (uint32_t)(v >> 32), slot0 = (uint32_t)(ex >> 32);
       long_seg[slot0] = make_uint2((uint32_t)i, nch);
-      arrive[slot0] = 0u;
       for (uint32_t c = 0; c < nch; ++c) {
         const uint32_t s = start + c * RTF_SEG_CHUNK;
+        arrive[slot0 + c] = 0u;   // [slot0]: the segment's counter, [slot0 + 1 + g]: group g's
         items[slot0 + c] = make_uint4(key, s, min((uint32_t)RTF_SEG_CHUNK, start + len - s), slot0);
       }
     }
@@ -532,30 +533,25 @@ struct SegWork {
   int dim_max;
 };
 
-// Last chunk of a long segment to arrive: add the chunk partials IN CHUNK ORDER (whoever runs
-// this, the summation tree is the same), then update the row.  Kept out of line: it is rare and
-// must not cost the streaming path registers.
+// acc = partials[first] + partials[first + stride] + ... (count terms), IN ORDER
 template <int VEC, int G, int VPL>
-__device__ __noinline__ void combine_long(const BwdParams& P, const SegWork& S, uint32_t key,
-                                          uint32_t slot0, uint2 ls, int nv, int lg) {
-  __threadfence();
-  if (lg == 0) S.arrive[slot0] = 0u;  // the prepared work list can be applied again
-  Vec<VEC> acc[VPL];
+__device__ __forceinline__ void sum_partials(const SegWork& S, uint32_t first, uint32_t count,
+                                             uint32_t stride, int nv, int lg, Vec<VEC> (&acc)[VPL]) {
 #pragma unroll
   for (int k = 0; k < VPL; ++k)
 #pragma unroll
     for (int e = 0; e < VEC; ++e) acc[k].v[e] = 0.f;
-  constexpr int U = 4;  // partials are contiguous and L2-resident
+  constexpr int U = 4;  // partials are L2-resident; 4 loads in flight
 #pragma unroll 1
-  for (uint32_t c0 = 0; c0 < ls.y; c0 += U) {
+  for (uint32_t c0 = 0; c0 < count; c0 += U) {
     Vec<VEC> x[U][VPL];
 #pragma unroll
     for (int u = 0; u < U; ++u)
 #pragma unroll
       for (int k = 0; k < VPL; ++k) {
         const int vi = lg + k * G;
-        if (c0 + u < ls.y && vi < nv) {
-          const float* src = S.partials + (long long)(slot0 + c0 + u) * S.dim_max + VEC * vi;
+        if (c0 + u < count && vi < nv) {
+          const float* src = S.partials + (long long)(first + (c0 + u) * stride) * S.dim_max + VEC * vi;
           if constexpr (VEC == 4) {
             const float4 t = __ldcg(reinterpret_cast<const float4*>(src));
             x[u][k].v[0] = t.x; x[u][k].v[1] = t.y; x[u][k].v[2] = t.z; x[u][k].v[3] = t.w;
@@ -566,7 +562,7 @@ __device__ __noinline__ void combine_long(const BwdParams& P, const SegWork& S, 
       }
 #pragma unroll
     for (int u = 0; u < U; ++u)
-      if (c0 + u < ls.y) {
+      if (c0 + u < count) {
 #pragma unroll
         for (int k = 0; k < VPL; ++k) {
           const int vi = lg + k * G;
@@ -577,6 +573,53 @@ __device__ __noinline__ void combine_long(const BwdParams& P, const SegWork& S, 
         }
       }
   }
+}
+
+// Combination of a long segment's chunk partials.  The summation tree depends only on the
+// segment's length, never on which thread runs it: chunks form GROUPS of RTF_SEG_GROUP; the last
+// chunk of a group to arrive adds the group's partials in chunk order and leaves the group sum in
+// the group's first slot; the last GROUP to finish adds the group sums in group order and updates
+// the row.  (One level was enough for the Criteo tables; a padding id that fills half of a
+// behaviour-sequence batch is a 200 000-row segment = 3 200 partials, which one lane group added
+// serially in 0.24 ms — half of the DIN step.)  Kept out of line: rare, and it must not cost the
+// streaming path registers.
+template <int VEC, int G, int VPL>
+__device__ __noinline__ void combine_long(const BwdParams& P, const SegWork& S, uint32_t key,
+                                          uint32_t slot0, uint32_t chunk, uint2 ls, int nv, int lg,
+                                          uint32_t gmask, int g0) {
+  const uint32_t nch = ls.y;
+  const uint32_t ngrp = (nch + RTF_SEG_GROUP - 1) / RTF_SEG_GROUP;
+  const uint32_t grp = chunk / RTF_SEG_GROUP;
+  const uint32_t gsz = min((uint32_t)RTF_SEG_GROUP, nch - grp * RTF_SEG_GROUP);
+  Vec<VEC> acc[VPL];
+  if (ngrp > 1) {
+    // arrive[slot0 + 1 + g] counts the chunks of group g (ngrp + 1 <= nch slots belong to us)
+    uint32_t t1 = 0;
+    if (lg == 0) t1 = atomicAdd(S.arrive + slot0 + 1 + grp, 1u);
+    t1 = __shfl_sync(gmask, t1, g0);
+    if (t1 != gsz - 1) return;
+    __threadfence();
+    if (lg == 0) S.arrive[slot0 + 1 + grp] = 0u;   // the prepared work list can be applied again
+    sum_partials<VEC, G, VPL>(S, slot0 + grp * RTF_SEG_GROUP, gsz, 1u, nv, lg, acc);
+#pragma unroll
+    for (int k = 0; k < VPL; ++k) {
+      const int vi = lg + k * G;
+      if (vi < nv)
+        vstore<VEC>(S.partials + (long long)(slot0 + grp * RTF_SEG_GROUP) * S.dim_max + VEC * vi, acc[k]);
+    }
+    __threadfence();
+    __syncwarp(gmask);
+  }
+  if (ngrp > 1) {       // (one group: the caller already holds the last ticket)
+    uint32_t t0 = 0;
+    if (lg == 0) t0 = atomicAdd(S.arrive + slot0, 1u);
+    t0 = __shfl_sync(gmask, t0, g0);
+    if (t0 != ngrp - 1) return;
+  }
+  __threadfence();
+  if (lg == 0) S.arrive[slot0] = 0u;
+  if (ngrp > 1) sum_partials<VEC, G, VPL>(S, slot0, ngrp, (uint32_t)RTF_SEG_GROUP, nv, lg, acc);
+  else sum_partials<VEC, G, VPL>(S, slot0, nch, 1u, nv, lg, acc);
   RowState<VEC, VPL> st;
   load_row_state<VEC, G, VPL>(P, key, nv, lg, st);
   finish_row<VEC, G, VPL>(P, key, ls.x, nv, lg, acc, st, S.uniq_key, S.uniq_grad, S.dim_max);
@@ -660,10 +703,13 @@ seg_apply(const __grid_constant__ BwdParams P, const __grid_constant__ SegWork S
   __threadfence();
   __syncwarp(gmask);
   const uint2 ls = __ldg(S.long_seg + slot0);  // (segment index, #chunks)
-  uint32_t ticket = 0;
-  if (lg == 0) ticket = atomicAdd(S.arrive + slot0, 1u);
-  ticket = __shfl_sync(gmask, ticket, g0);
-  if (ticket == ls.y - 1) combine_long<VEC, G, VPL>(P, S, key, slot0, ls, nv, lg);
+  if (ls.y <= RTF_SEG_GROUP) {   // one level: the ticket is taken here, the rare winner goes out of line
+    uint32_t ticket = 0;
+    if (lg == 0) ticket = atomicAdd(S.arrive + slot0, 1u);
+    ticket = __shfl_sync(gmask, ticket, g0);
+    if (ticket != ls.y - 1) return;
+  }
+  combine_long<VEC, G, VPL>(P, S, key, slot0, i - slot0, ls, nv, lg, gmask, g0);
 }
 
 template <int VEC, int G, int VPL, int MINB>

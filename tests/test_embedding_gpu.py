@@ -165,6 +165,10 @@ BWD_CASES = [
     ("pool_mean", 40, [30, 300], [32, 32], [0, 1], 9, "mean"),
     ("mixed_dims", 70, [10, 20, 30], [4, 64, 256], [0, 1, 2], 1, None),
     ("odd_dims_scalar", 90, [11, 13], [3, 10], [0, 1], 2, None),
+    # > RTF_SEG_CHUNK * RTF_SEG_GROUP = 4096 lookups of one row (a padding id in a behaviour
+    # sequence): chunk partials are combined per group of 64 chunks, then the groups
+    ("giant_segments_d8_seq", 600, [2, 40], [8, 8], [0, 1], 20, None),
+    ("giant_segments_d128", 9000, [1, 3], [128, 128], [0, 1], 1, None),
 ]
 
 
@@ -201,8 +205,8 @@ def test_grad_segments_bit_exact(rtf, case):
 
 
 @pytest.mark.parametrize("kind", ["sgd", "adagrad", "adam"])
-@pytest.mark.parametrize("case", [BWD_CASES[0], BWD_CASES[1], BWD_CASES[3], BWD_CASES[5], BWD_CASES[7]],
-                         ids=lambda c: c[0])
+@pytest.mark.parametrize("case", [BWD_CASES[0], BWD_CASES[1], BWD_CASES[3], BWD_CASES[5], BWD_CASES[7],
+                                  BWD_CASES[8]], ids=lambda c: c[0])
 def test_sparse_optimizer_in_place_bit_exact(rtf, kind, case):
     name, B, rows, dims, ft, L, pool = case
     rng, ids, grad = _bwd_inputs(case, seed=4)
@@ -339,3 +343,30 @@ def test_dense_adam_matches_keras_formula(rtf):
             r.sub_(lr_t * m_ / (v_.sqrt() + 1e-7))
     for p, r in zip(ps, ref):
         torch.testing.assert_close(p.detach().double().cpu(), r, rtol=1e-5, atol=1e-6)
+
+
+def test_prepared_work_list_can_be_applied_twice_incl_giant_segments(rtf):
+    """K2 split (prepare on the ids, apply on the gradient): the work list of one batch is applied
+    twice (the multi-GPU path reduces, then updates) — the arrival counters of long segments, incl.
+    the two-level ones, must be back at zero after every apply.  Sums equal the one-shot K2's."""
+    case = ("giant", 5000, [1, 7, 3000], [32, 32, 32], [0, 1, 2], 2, None)
+    rng, ids, grad = _bwd_inputs(case)
+    name, B, rows, dims, ft, L, pool = case
+    dids = torch.from_numpy(ids).to(torch.int32).cuda()          # (B, F, L)
+    g = torch.from_numpy(grad).cuda()
+    ts = rtf.EmbeddingTables(rows, dims, seed=1, optimizer=rtf.SparseOptimizer("sgd", lr=0.0))
+    weights = [torch.zeros(n, d, device="cuda") for n, d in zip(rows, dims)]
+    keys_w, tot_w, rb = rtf.embed_bwd(weights, ft, dids, g, "BFL", None, want_unique=True)
+    h = ts.prepare_backward(dids, ft, "BFL")
+    n = B * L * len(ft)
+    outs = []
+    for _ in range(2):
+        uk = torch.full((n,), -1, dtype=torch.int32, device="cuda")
+        ug = torch.zeros((n, max(dims)), device="cuda")
+        ts.apply_prepared(h, g, None, reduce_only=(uk, ug))
+        torch.cuda.synchronize()
+        k = keys_w.numel()
+        outs.append((uk[:k].clone(), ug[:k].clone()))
+    assert torch.equal(outs[0][0], outs[1][0]) and torch.equal(outs[0][1], outs[1][1])
+    assert torch.equal(outs[0][0].to(torch.int64) & 0xFFFFFFFF, keys_w)
+    assert torch.equal(outs[0][1], tot_w)
