@@ -359,6 +359,20 @@ int rtf_bn_bwd(const float* d_dy, int64_t lddy, const float* d_x, int64_t ldx, i
                int64_t lddx, float* d_dgamma, float* d_dbeta, void* d_ws, size_t ws_bytes,
                void* stream);
 
+/* ---- LayerNormalization of the TransformerEncoder block (either side of K7) ----
+ * replaces: tensorflow.keras.layers.LayerNormalization(epsilon) in
+ *           src/match/layers/modules.py:173-185 (last axis, biased variance, App. A8) + gradient.
+ * contiguous (rows, C), C <= 256: a warp per row (two-pass mean / centred variance in registers);
+ * dgamma / dbeta are deterministic two-stage column sums.  NULL allowed: gamma, beta, dx,
+ * dgamma, dbeta.                                                                               */
+int rtf_layernorm_workspace(int64_t rows, int C, size_t* bytes);
+int rtf_layernorm_fwd(const float* d_x, int64_t rows, int C, const float* d_gamma,
+                      const float* d_beta, float eps, float* d_y, float* d_mean, float* d_rstd,
+                      void* stream);
+int rtf_layernorm_bwd(const float* d_dy, const float* d_x, const float* d_mean, const float* d_rstd,
+                      const float* d_gamma, int64_t rows, int C, float* d_dx, float* d_dgamma,
+                      float* d_dbeta, void* d_ws, size_t ws_bytes, void* stream);
+
 /* ---- dense-layer GEMMs (MLP either side of the path) --------------------------
  * replaces: the MatMul (+BiasAdd+Relu) of tensorflow.keras.layers.Dense inside
  *           ctr.layers.modules.DNN (src/ctr/layers/modules.py:114-135) and its two gradient

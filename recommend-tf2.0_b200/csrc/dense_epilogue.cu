@@ -9,19 +9,20 @@
 
 namespace rtf {
 
-constexpr int RB_ROWS = 128;
+constexpr int RB_ROWS = 128;       // rows per chunk up to B = 65 536 (512 chunks); larger batches take
+constexpr int RB_MAX_CHUNKS = 512; // proportionally longer chunks so that stage 2 stays short
 
 // CTA = lx column lanes (float4 each) x 128/lx row lanes; a row lane owns RB_ROWS/(128/lx)
 // consecutive rows of the chunk and writes its own partial row, so narrow layers (N = 128: 32
 // column lanes) still fill the CTA
 __global__ void __launch_bounds__(128)
 relu_bwd_colsum_stage1(const float* __restrict__ gy, const float* __restrict__ y, long long B,
-                       int Ccols, int lx, float* __restrict__ g, float* __restrict__ partial) {
+                       int Ccols, int lx, int rb, float* __restrict__ g, float* __restrict__ partial) {
   const int tx = threadIdx.x % lx, ty = threadIdx.x / lx, ny = 128 / lx;
   const int c4 = (blockIdx.x * lx + tx) * 4;
   if (c4 >= Ccols) return;
-  const int sub = RB_ROWS / ny;
-  const long long b0 = (long long)blockIdx.y * RB_ROWS + (long long)ty * sub;
+  const int sub = rb / ny;
+  const long long b0 = (long long)blockIdx.y * rb + (long long)ty * sub;
   const long long b1 = min(b0 + sub, B);
   float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
   for (long long b = b0; b < b1; ++b) {
@@ -75,6 +76,11 @@ relu_bwd_colsum_stage2(const float* __restrict__ partial, int nchunks, int Ccols
 
 using namespace rtf;
 
+static int relu_bwd_rb(long long B) {   // rows per chunk: 128 * ceil(B / 65 536)
+  const long long per = (long long)RB_ROWS * RB_MAX_CHUNKS;
+  return (int)(RB_ROWS * ((B + per - 1) / per > 0 ? (B + per - 1) / per : 1));
+}
+
 static int relu_bwd_lx(int cols) {   // column lanes per CTA: 32, 64 or 128
   const int v = cols / 4;
   return v <= 32 ? 32 : (v <= 64 ? 64 : 128);
@@ -83,7 +89,8 @@ static int relu_bwd_lx(int cols) {   // column lanes per CTA: 32, 64 or 128
 extern "C" int rtf_relu_bwd_colsum_workspace(int64_t B, int cols, size_t* bytes) {
   if (!bytes || B < 0 || cols <= 0) return RTF_E_ARG;
   const size_t ny = 128 / relu_bwd_lx(cols);
-  *bytes = (size_t)((B + RB_ROWS - 1) / RB_ROWS + 1) * ny * (size_t)cols * 4;
+  const int rb = relu_bwd_rb(B);
+  *bytes = (size_t)((B + rb - 1) / rb + 1) * ny * (size_t)cols * 4;
   return 0;
 }
 
@@ -98,10 +105,11 @@ extern "C" int rtf_relu_bwd_colsum(const float* d_gy, const float* d_y, int64_t 
   if (cols % 4 || (uintptr_t)d_gy % 16 || (uintptr_t)d_y % 16 || (uintptr_t)d_g % 16 ||
       (uintptr_t)d_ws % 16)
     return RTF_E_ALIGN;
-  const int nchunks = (int)((B + RB_ROWS - 1) / RB_ROWS);
+  const int rb = relu_bwd_rb(B);
+  const int nchunks = (int)((B + rb - 1) / rb);
   const int lx = relu_bwd_lx(cols), ny = 128 / lx;
   dim3 g1((cols / 4 + lx - 1) / lx, nchunks);
-  relu_bwd_colsum_stage1<<<g1, 128, 0, st>>>(d_gy, d_y, B, cols, lx, d_g, (float*)d_ws);
+  relu_bwd_colsum_stage1<<<g1, 128, 0, st>>>(d_gy, d_y, B, cols, lx, rb, d_g, (float*)d_ws);
   relu_bwd_colsum_stage2<<<(cols + 31) / 32, 256, 0, st>>>((const float*)d_ws, nchunks * ny, cols,
                                                            d_colsum);
   RTF_CHECK_LAUNCH();

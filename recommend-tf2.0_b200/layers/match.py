@@ -24,6 +24,50 @@ class DNN(_CoreDNN):
         super().__init__(hidden_units, activation, dnn_dropout, input_bn=False, **kwargs)
 
 
+class _LayerNormFn(torch.autograd.Function):
+    """rtf_layernorm_fwd / rtf_layernorm_bwd: a warp per row, dgamma / dbeta as deterministic
+    two-stage column sums (the framework kernel runs one CTA per 64-float row: 0.3 TB/s)."""
+
+    @staticmethod
+    def forward(ctx, x, gamma, beta, eps):
+        from ..core import _scratch
+        L.require_cuda(x, "LayerNormalization(x)")
+        Cc = x.shape[-1]
+        x2 = x.reshape(-1, Cc)
+        if not x2.is_contiguous():
+            x2 = x2.contiguous()
+        rows = x2.shape[0]
+        y = torch.empty_like(x2)
+        stats = torch.empty((2, rows), dtype=torch.float32, device=x.device)
+        L.check(L.lib().rtf_layernorm_fwd(x2.data_ptr(), rows, Cc, gamma.data_ptr(), beta.data_ptr(), eps,
+                                          y.data_ptr(), stats[0].data_ptr(), stats[1].data_ptr(),
+                                          L.current_stream_ptr()), "rtf_layernorm_fwd")
+        ctx.save_for_backward(x2, stats, gamma)
+        ctx.shape = x.shape
+        ctx._scratch = _scratch
+        return y.view(x.shape)
+
+    @staticmethod
+    def backward(ctx, dy):
+        x2, stats, gamma = ctx.saved_tensors
+        rows, Cc = x2.shape
+        dy2 = dy.reshape(rows, Cc)
+        if not dy2.is_contiguous():
+            dy2 = dy2.contiguous()
+        nb = C.c_size_t(0)
+        L.check(L.lib().rtf_layernorm_workspace(rows, Cc, C.byref(nb)), "rtf_layernorm_workspace")
+        ws = ctx._scratch(nb.value, dy.device)
+        dx = torch.empty_like(x2) if ctx.needs_input_grad[0] else None
+        dg = torch.empty(Cc, dtype=torch.float32, device=dy.device)
+        db = torch.empty(Cc, dtype=torch.float32, device=dy.device)
+        L.check(L.lib().rtf_layernorm_bwd(dy2.data_ptr(), x2.data_ptr(), stats[0].data_ptr(),
+                                          stats[1].data_ptr(), gamma.data_ptr(), rows, Cc,
+                                          None if dx is None else dx.data_ptr(), dg.data_ptr(),
+                                          db.data_ptr(), ws.data_ptr(), ws.numel(),
+                                          L.current_stream_ptr()), "rtf_layernorm_bwd")
+        return (None if dx is None else dx.view(ctx.shape)), dg, db, None
+
+
 class LayerNormalization(Layer):
     """Keras LayerNormalization(epsilon): last axis, biased variance, gamma=1 / beta=0 (A8)."""
 
@@ -37,6 +81,9 @@ class LayerNormalization(Layer):
         self.beta = self.add_weight("beta", (c,), "zeros")
 
     def call(self, x, **kwargs):
+        if x.is_cuda and x.dtype == torch.float32 and x.shape[-1] <= 256 and x.numel() > 0:
+            return _LayerNormFn.apply(x, self.gamma, self.beta, self.epsilon)
+        # wider rows than the warp-per-row kernel takes (or CPU tensors in the layer-building tests)
         return F.layer_norm(x, (x.shape[-1],), self.gamma, self.beta, self.epsilon)
 
 

@@ -445,6 +445,7 @@ def test_sasrec_score_kernel_vs_oracle_fwd_bwd(rtf, B, NEG, D, N):
 
 def test_sasrec_fused_scores_match_unfused_training(rtf):
     from recommend_tf2_b200.models import SASRec
+    torch.manual_seed(123)          # fixed inputs: three Adam steps at lr 1e-2 amplify any difference
     seq = torch.randint(1, 100, (8, 10), device="cuda", dtype=torch.int32)
     seq[:, :4] = 0
     pos = torch.randint(1, 100, (8, 1), device="cuda", dtype=torch.int32)
