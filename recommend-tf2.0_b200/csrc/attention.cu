@@ -182,6 +182,148 @@ __global__ void __launch_bounds__(ATT_FWD_THREADS, 1) attn_fwd_kernel(const __gr
   }
 }
 
+// Forward for hs % 8 == 0, hs >= 32 (the SASRec shape: L = 200, hs = 64): bigger register tiles.
+// On the CUDA cores a shared-memory load costs one wavefront per 128 bytes delivered to the warp —
+// broadcast or not — and the SM moves one wavefront per clock against four FFMA warp
+// instructions, so an r x c register tile (r + c words per r*c FMAs) has to be large.  The kernel
+// above runs QK^T on 4 x 7 tiles (0.39 wavefronts per FMA) and P.V on 4 x 2 (0.75): it is bound by
+// operand delivery at ~0.2 of the FMA peak.  Here a warp owns EIGHT query rows: QK^T on 8 x KPL
+// tiles (0.27), and P.V with lane = (column group cg, key group jg): a lane accumulates 8 rows x 8
+// columns over the keys j = jg, jg + JG, ... (16 words per 64 FMAs: 0.25) and the JG partial tiles
+// are added by xor-shuffles (fixed order).  The lane's 8 columns are two float4 groups hs/2 apart,
+// so a quarter-warp reads 128 contiguous bytes of a V row (conflict-free).
+constexpr int ATT_R8 = 8;
+template <int KPL, int CG>
+__global__ void __launch_bounds__(448, 1) attn_fwd8_kernel(const __grid_constant__ AttnParams P) {
+  extern __shared__ __align__(16) float smem[];
+  constexpr int R = ATT_R8, JG = 32 / CG;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int b = blockIdx.x / P.H, h = blockIdx.x - b * P.H;
+  const int hs = P.hs, Lq = P.Lq, Lk = P.Lk, RS = hs + 4;
+  float* Ks = smem;                       // [Lk][RS]
+  float* Vs = Ks + Lk * RS;               // [Lk][RS]
+  float* Qw = Vs + Lk * RS + warp * (R * hs + Lk * R);  // per warp: Q rows [R][hs]
+  float* Pw = Qw + R * hs;                               // per warp: P^T [Lk][R]
+  load_tile(Ks, RS, P.k + (long long)b * P.k_sb + h * hs, P.k_sl, Lk, hs);
+  load_tile(Vs, RS, P.v + (long long)b * P.v_sb + h * hs, P.v_sl, Lk, hs);
+  __syncthreads();
+  const float* qb = P.q + (long long)b * P.q_sb + h * hs;
+  const int cg = lane & (CG - 1), jg = lane / CG;
+  const int c0 = 4 * cg, c1 = (hs >> 1) + 4 * cg;   // the lane's two column groups
+  const bool col_ok = c0 < (hs >> 1);
+  for (int i0 = warp * R; i0 < Lq; i0 += (blockDim.x >> 5) * R) {
+    for (int e = lane; e < R * hs; e += 32) {
+      const int r = e / hs, c = e - r * hs;
+      Qw[e] = (i0 + r < Lq) ? qb[(long long)(i0 + r) * P.q_sl + c] : 0.f;
+    }
+    __syncwarp();
+    float acc[R][KPL];
+#pragma unroll
+    for (int r = 0; r < R; ++r)
+#pragma unroll
+      for (int t = 0; t < KPL; ++t) acc[r][t] = 0.f;
+    for (int d = 0; d < hs; d += 4) {
+      float4 qv[R];
+#pragma unroll
+      for (int r = 0; r < R; ++r) qv[r] = *reinterpret_cast<const float4*>(Qw + r * hs + d);
+#pragma unroll
+      for (int t = 0; t < KPL; ++t) {
+        const int j = lane + 32 * t;
+        if (j < Lk) {
+          const float4 kv = *reinterpret_cast<const float4*>(Ks + j * RS + d);
+#pragma unroll
+          for (int r = 0; r < R; ++r) {
+            acc[r][t] = fmaf(qv[r].x, kv.x, acc[r][t]);
+            acc[r][t] = fmaf(qv[r].y, kv.y, acc[r][t]);
+            acc[r][t] = fmaf(qv[r].z, kv.z, acc[r][t]);
+            acc[r][t] = fmaf(qv[r].w, kv.w, acc[r][t]);
+          }
+        }
+      }
+    }
+    // masks + softmax per row (same arithmetic and order as attn_fwd_kernel)
+#pragma unroll
+    for (int r = 0; r < R; ++r) {
+      const int i = i0 + r;
+      const bool row_ok = !P.row_mask || (i < Lq && P.row_mask[(long long)b * P.rm_sb + i] != 0.f);
+      float m = -INFINITY;
+#pragma unroll
+      for (int t = 0; t < KPL; ++t) {
+        const int j = lane + 32 * t;
+        if (j < Lk) {
+          const bool key_ok = !P.key_mask || P.key_mask[(long long)b * P.km_sb + j] != 0.f;
+          acc[r][t] = mask_logit(acc[r][t] * P.scale, row_ok, key_ok, !P.causal || j <= i);
+          m = fmaxf(m, acc[r][t]);
+        }
+      }
+      m = warp_max(m);
+      float l = 0.f;
+#pragma unroll
+      for (int t = 0; t < KPL; ++t) {
+        const int j = lane + 32 * t;
+        if (j < Lk) {
+          acc[r][t] = expf(acc[r][t] - m);
+          l += acc[r][t];
+        }
+      }
+      l = warp_sum(l);
+      const float il = 1.f / l;
+#pragma unroll
+      for (int t = 0; t < KPL; ++t) {
+        const int j = lane + 32 * t;
+        if (j < Lk) Pw[j * R + r] = acc[r][t] * il;
+      }
+      if (lane == 0 && i < Lq && P.stat_m) {
+        const long long si = ((long long)b * P.H + h) * Lq + i;
+        P.stat_m[si] = m;
+        P.stat_il[si] = il;
+      }
+    }
+    __syncwarp();
+    // O = P V: 8 rows x 8 columns per lane over the keys of its key group
+    float o[R][8];
+#pragma unroll
+    for (int r = 0; r < R; ++r)
+#pragma unroll
+      for (int c = 0; c < 8; ++c) o[r][c] = 0.f;
+    if (col_ok) {
+#pragma unroll 2
+      for (int j = jg; j < Lk; j += JG) {
+        const float4 p0 = *reinterpret_cast<const float4*>(Pw + j * R);
+        const float4 p1 = *reinterpret_cast<const float4*>(Pw + j * R + 4);
+        const float4 v0 = *reinterpret_cast<const float4*>(Vs + j * RS + c0);
+        const float4 v1 = *reinterpret_cast<const float4*>(Vs + j * RS + c1);
+        const float pr[R] = {p0.x, p0.y, p0.z, p0.w, p1.x, p1.y, p1.z, p1.w};
+        const float vc[8] = {v0.x, v0.y, v0.z, v0.w, v1.x, v1.y, v1.z, v1.w};
+#pragma unroll
+        for (int r = 0; r < R; ++r)
+#pragma unroll
+          for (int c = 0; c < 8; ++c) o[r][c] = fmaf(pr[r], vc[c], o[r][c]);
+      }
+    }
+#pragma unroll
+    for (int off = CG; off < 32; off <<= 1)
+#pragma unroll
+      for (int r = 0; r < R; ++r)
+#pragma unroll
+        for (int c = 0; c < 8; ++c) o[r][c] += __shfl_xor_sync(0xffffffffu, o[r][c], off);
+    if (jg == 0 && col_ok) {
+      float* ob = P.out + (long long)b * P.o_sb + h * hs;
+#pragma unroll
+      for (int r = 0; r < R; ++r)
+        if (i0 + r < Lq) {
+          float* orow = ob + (long long)(i0 + r) * P.o_sl;
+#pragma unroll
+          for (int c = 0; c < 4; ++c) {
+            orow[c0 + c] = o[r][c];
+            orow[c1 + c] = o[r][4 + c];
+          }
+        }
+    }
+    __syncwarp();
+  }
+}
+
 // ----------------------------------------------------------------------------- backward: dQ
 // rows owned by warps (as forward): recompute P, dP = dO V^T, dS = P (dP - delta), dQ = scale dS K
 template <int KPL>
@@ -497,6 +639,30 @@ extern "C" int rtf_attn_fwd(const float* d_q, int64_t q_sb, int64_t q_sl, const 
   const int thr = warps * 32;
   cudaStream_t st = (cudaStream_t)stream;
   const int kpl = (Lk + 31) / 32;
+  if (hs % 8 == 0 && hs >= 32 && Lq >= 64) {
+    // 8 query rows per warp (see attn_fwd8_kernel); warps = what the per-warp staging leaves room
+    // for, at most 14 (448 threads x 144 registers), no more than there are row blocks
+    auto smem8 = [&](int w) { return ((size_t)2 * Lk * RS + (size_t)w * (ATT_R8 * hs + Lk * ATT_R8)) * 4; };
+    int w8 = 14;
+    while (w8 > 2 && smem8(w8) > 227 * 1024) --w8;
+    const int blocks8 = (Lq + ATT_R8 - 1) / ATT_R8;
+    if (w8 > blocks8) w8 = blocks8;
+    // even out the last round: 25 row blocks over 14 warps = 2 rounds -> 13 warps do the same
+    const int rounds = (blocks8 + w8 - 1) / w8;
+    w8 = (blocks8 + rounds - 1) / rounds;
+    if (smem8(w8) <= 227 * 1024) {
+      const size_t sm8 = smem8(w8);
+      const int cgn = hs / 8;   // column groups: 4, 8 or 16 (hs = 32..128)
+#define RTF_FWD8(K)                                                                              \
+  (cgn <= 4 ? attn_launch(attn_fwd8_kernel<K, 4>, P, sm8, w8 * 32, st)                           \
+            : cgn <= 8 ? attn_launch(attn_fwd8_kernel<K, 8>, P, sm8, w8 * 32, st)                \
+                       : attn_launch(attn_fwd8_kernel<K, 16>, P, sm8, w8 * 32, st))
+      if (kpl <= 2) return RTF_FWD8(2);
+      if (kpl <= 4) return RTF_FWD8(4);
+      return RTF_FWD8(8);
+#undef RTF_FWD8
+    }
+  }
   if (kpl <= 1) return attn_launch(attn_fwd_kernel<1>, P, smem, thr, st);
   if (kpl <= 2) return attn_launch(attn_fwd_kernel<2>, P, smem, thr, st);
   if (kpl <= 4) return attn_launch(attn_fwd_kernel<4>, P, smem, thr, st);
