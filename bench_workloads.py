@@ -242,7 +242,7 @@ class SASRec(Workload):
         rm = (dev[0][0] != 0).float()
         with torch.no_grad():
             ms = _timed(lambda i: pkg.attention(qkv, qkv, qkv, 1, 1.0 / math.sqrt(d), row_mask=rm), 6)
-        return _fma_roof("attn_fwd_kernel (K7 forward: QK^T / sqrt d, query-row mask, softmax, PV; L=200, d=64)",
+        return _fma_roof("attn_fwd8_kernel (K7 forward: QK^T / sqrt d, query-row mask, softmax, PV; L=200, d=64)",
                          ms, B * 2 * (L * L * d * 2))
 
     def cpu_model(self):
