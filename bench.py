@@ -72,7 +72,8 @@ def parse_args():
     ap.add_argument("--no-kernel-timing", action="store_true")
     ap.add_argument("--cuda-graph", default="auto", choices=["auto", "on", "off"],
                     help="replay the training step from a CUDA graph (core.StepGraph). auto = on for "
-                         "the launch-bound workloads (fm, din, autoint, youtubednn), off elsewhere")
+                         "single-GPU dlrm and the launch-bound workloads (fm, din, autoint, youtubednn), "
+                         "off for sasrec and for multi-GPU runs")
     return ap.parse_args()
 
 
@@ -174,7 +175,10 @@ def bench_config(args, world):
             "rows_total": sum(CRITEO_ROWS), "embed_dim": EMBED_DIM, "bot_mlp": list(BOT_MLP),
             "top_mlp": list(TOP_MLP), "interaction": "dot", "batch_per_gpu": args.batch,
             "global_batch": args.batch * world, "ids": args.ids,
-            "optimizer": "adam (sparse rows fused in K2, dense MLP torch fused)",
+            "optimizer": "adam (sparse rows fused in K2, dense MLP rtf_dense_adam)",
+            "cuda_graph": ("step replayed from one CUDA graph (batch copied into static buffers, Adam "
+                           "step size read from a device scalar)"
+                           if world == 1 and args.cuda_graph != "off" else "off (eager launches)"),
             "l2_flush": "inputs larger than L2: 17.2 GB of tables, distinct batch every step",
             "parallelism": "single" if world == 1 else
             f"tables sharded over {world} GPUs ({args.exchange} row exchange"
@@ -437,7 +441,11 @@ def run_b200(args):
     fc = pkg.criteo_feature_columns(EMBED_DIM, rows=CRITEO_ROWS)
     if world == 1:
         model = pkg.DLRM(fc, BOT_MLP, TOP_MLP, interaction="dot", seed=1234, pad_to=args.pad_to)
-        trainer = pkg.DLRMTrainer(model, lr=1e-3)
+        # the step is replayed from one CUDA graph: the GPU is the bound at this batch size, but the
+        # host needs 4-5 ms per 7.7 ms step to enqueue it eagerly and measured 8-14 ms on a busy box
+        # (the step then runs at the host's pace); a replay costs it ~0.1 ms
+        use_graph = args.cuda_graph != "off"
+        trainer = pkg.DLRMTrainer(model, lr=1e-3, cuda_graph=use_graph)
     else:
         from recommend_tf2_b200.sharded import (PeerShardedDLRM, ShardedDLRM, ShardedDLRMTrainer,
                                                 all_ranks_ok, parity_self_check)
@@ -488,6 +496,11 @@ def run_b200(args):
     # them): its embedding exchange is pipelined behind the current step (sharded.py prefetch)
     pipelined = world > 1 and not args.no_pipeline
     nxt = (lambda i: {"next_sparse": dev[i + 1][1]} if pipelined and i + 1 < len(dev) else {})
+    graphed = world == 1 and trainer.graph is not None
+    if graphed:             # the eager steps and the capture happen before the W warm-up steps
+        for i in range(4):
+            trainer.step(*dev[i % W])
+        assert trainer.graph.graph is not None
     for i in range(W):
         trainer.step(*dev[i], **nxt(i))
     barrier()
