@@ -324,9 +324,57 @@ __global__ void __launch_bounds__(448, 1) attn_fwd8_kernel(const __grid_constant
   }
 }
 
+// ---- "P.V"-shaped products on 4 x 8 lane tiles (backward kernels, hs % 8 == 0, hs >= 32) ------
+// o[r][c] += sum_j A[j][r] * T[j][col(c)] over the lane's key group j = jg, jg + JG, ...; A is a
+// per-warp [L][4] stage (P^T or dS^T), T a [L][RS] tile in shared memory; the lane's 8 columns are
+// the float4 groups at c0 and c1 = hs/2 + c0 (a quarter-warp reads 128 contiguous bytes).  12
+// words per 32 FMAs instead of the column-per-lane form's 6 per 8 (see attn_fwd8_kernel).
+template <int CG>
+__device__ __forceinline__ void pv_tile4(const float* __restrict__ A, const float* __restrict__ T,
+                                         int L, int RS, int c0, int c1, int jg, float (&o)[4][8]) {
+  constexpr int JG = 32 / CG;
+#pragma unroll 2
+  for (int j = jg; j < L; j += JG) {
+    const float4 a = *reinterpret_cast<const float4*>(A + j * 4);
+    const float4 t0 = *reinterpret_cast<const float4*>(T + j * RS + c0);
+    const float4 t1 = *reinterpret_cast<const float4*>(T + j * RS + c1);
+    const float ar[4] = {a.x, a.y, a.z, a.w};
+    const float tc[8] = {t0.x, t0.y, t0.z, t0.w, t1.x, t1.y, t1.z, t1.w};
+#pragma unroll
+    for (int r = 0; r < 4; ++r)
+#pragma unroll
+      for (int c = 0; c < 8; ++c) o[r][c] = fmaf(ar[r], tc[c], o[r][c]);
+  }
+}
+// add the key groups' partial tiles (xor-shuffles: fixed order) and let key group 0 store rows
+// row0 .. row0+3 (< nrows) of the (.., hs) output
+template <int CG>
+__device__ __forceinline__ void pv_reduce_store4(float (&o)[4][8], float* __restrict__ dst,
+                                                 long long stride, int row0, int nrows, int c0,
+                                                 int c1, bool writer) {
+#pragma unroll
+  for (int off = CG; off < 32; off <<= 1)
+#pragma unroll
+    for (int r = 0; r < 4; ++r)
+#pragma unroll
+      for (int c = 0; c < 8; ++c) o[r][c] += __shfl_xor_sync(0xffffffffu, o[r][c], off);
+  if (writer) {
+#pragma unroll
+    for (int r = 0; r < 4; ++r)
+      if (row0 + r < nrows) {
+        float* d = dst + (long long)(row0 + r) * stride;
+#pragma unroll
+        for (int c = 0; c < 4; ++c) {
+          d[c0 + c] = o[r][c];
+          d[c1 + c] = o[r][4 + c];
+        }
+      }
+  }
+}
+
 // ----------------------------------------------------------------------------- backward: dQ
 // rows owned by warps (as forward): recompute P, dP = dO V^T, dS = P (dP - delta), dQ = scale dS K
-template <int KPL>
+template <int KPL, int CG>   // CG > 0: hs / 8 column groups (4 x 8 lane tiles for dQ = dS K)
 __global__ void __launch_bounds__(ATT_DQ_THREADS, 1) attn_bwd_dq_kernel(const __grid_constant__ AttnParams P) {
   extern __shared__ __align__(16) float smem[];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -417,42 +465,55 @@ __global__ void __launch_bounds__(ATT_DQ_THREADS, 1) attn_bwd_dq_kernel(const __
       }
     }
     __syncwarp();
-    float o[ATT_R][4];
-#pragma unroll
-    for (int r = 0; r < ATT_R; ++r)
-#pragma unroll
-      for (int t = 0; t < 4; ++t) o[r][t] = 0.f;
-    for (int j = 0; j < Lk; ++j) {
-      const float4 p = *reinterpret_cast<const float4*>(Sw + j * ATT_R);
-#pragma unroll
-      for (int t = 0; t < 4; ++t) {
-        const int c = lane + 32 * t;
-        if (t < CT && c < hs) {
-          const float kk = Ks[j * RS + c];
-          o[0][t] = fmaf(p.x, kk, o[0][t]);
-          o[1][t] = fmaf(p.y, kk, o[1][t]);
-          o[2][t] = fmaf(p.z, kk, o[2][t]);
-          o[3][t] = fmaf(p.w, kk, o[3][t]);
-        }
-      }
-    }
     float* gq = P.dq + (long long)b * P.dq_sb + h * hs;
+    if constexpr (CG > 0) {
+      const int cg = lane & (CG - 1), jg = lane / CG;
+      const int c0 = 4 * cg, c1 = (hs >> 1) + 4 * cg;
+      const bool col_ok = c0 < (hs >> 1);
+      float o8[4][8];
 #pragma unroll
-    for (int r = 0; r < ATT_R; ++r)
-      if (i0 + r < Lq) {
+      for (int r = 0; r < 4; ++r)
+#pragma unroll
+        for (int c = 0; c < 8; ++c) o8[r][c] = 0.f;
+      if (col_ok) pv_tile4<CG>(Sw, Ks, Lk, RS, c0, c1, jg, o8);
+      pv_reduce_store4<CG>(o8, gq, P.dq_sl, i0, Lq, c0, c1, jg == 0 && col_ok);
+    } else {
+      float o[ATT_R][4];
+#pragma unroll
+      for (int r = 0; r < ATT_R; ++r)
+#pragma unroll
+        for (int t = 0; t < 4; ++t) o[r][t] = 0.f;
+      for (int j = 0; j < Lk; ++j) {
+        const float4 p = *reinterpret_cast<const float4*>(Sw + j * ATT_R);
 #pragma unroll
         for (int t = 0; t < 4; ++t) {
           const int c = lane + 32 * t;
-          if (t < CT && c < hs) gq[(long long)(i0 + r) * P.dq_sl + c] = o[r][t];
+          if (t < CT && c < hs) {
+            const float kk = Ks[j * RS + c];
+            o[0][t] = fmaf(p.x, kk, o[0][t]);
+            o[1][t] = fmaf(p.y, kk, o[1][t]);
+            o[2][t] = fmaf(p.z, kk, o[2][t]);
+            o[3][t] = fmaf(p.w, kk, o[3][t]);
+          }
         }
       }
+#pragma unroll
+      for (int r = 0; r < ATT_R; ++r)
+        if (i0 + r < Lq) {
+#pragma unroll
+          for (int t = 0; t < 4; ++t) {
+            const int c = lane + 32 * t;
+            if (t < CT && c < hs) gq[(long long)(i0 + r) * P.dq_sl + c] = o[r][t];
+          }
+        }
+    }
     __syncwarp();
   }
 }
 
 // ----------------------------------------------------------------------------- backward: dK, dV
 // keys owned by warps; the Q and dO tiles live in shared memory; lanes own queries
-template <int QPL>
+template <int QPL, int CG>   // CG > 0: 4 x 8 lane tiles for dV = P^T dO and dK = dS^T Q
 __global__ void __launch_bounds__(ATT_DKV_THREADS, 1) attn_bwd_dkv_kernel(const __grid_constant__ AttnParams P) {
   extern __shared__ __align__(16) float smem[];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -543,44 +604,63 @@ __global__ void __launch_bounds__(ATT_DKV_THREADS, 1) attn_bwd_dkv_kernel(const 
       }
     }
     __syncwarp();
-    float gk[ATT_R][4], gv[ATT_R][4];
-#pragma unroll
-    for (int r = 0; r < ATT_R; ++r)
-#pragma unroll
-      for (int t = 0; t < 4; ++t) gk[r][t] = gv[r][t] = 0.f;
-    for (int i = 0; i < Lq; ++i) {
-      const float4 p = *reinterpret_cast<const float4*>(Pw + i * ATT_R);
-      const float4 ds = *reinterpret_cast<const float4*>(Sw + i * ATT_R);
-#pragma unroll
-      for (int t = 0; t < 4; ++t) {
-        const int c = lane + 32 * t;
-        if (t < CT && c < hs) {
-          const float qq = Qs[i * RS + c], gg = Ds[i * RS + c];
-          gv[0][t] = fmaf(p.x, gg, gv[0][t]);
-          gv[1][t] = fmaf(p.y, gg, gv[1][t]);
-          gv[2][t] = fmaf(p.z, gg, gv[2][t]);
-          gv[3][t] = fmaf(p.w, gg, gv[3][t]);
-          gk[0][t] = fmaf(ds.x, qq, gk[0][t]);
-          gk[1][t] = fmaf(ds.y, qq, gk[1][t]);
-          gk[2][t] = fmaf(ds.z, qq, gk[2][t]);
-          gk[3][t] = fmaf(ds.w, qq, gk[3][t]);
-        }
-      }
-    }
     float* gkb = P.dk + (long long)b * P.dk_sb + h * hs;
     float* gvb = P.dv + (long long)b * P.dv_sb + h * hs;
+    if constexpr (CG > 0) {
+      const int cg = lane & (CG - 1), ig = lane / CG;
+      const int c0 = 4 * cg, c1 = (hs >> 1) + 4 * cg;
+      const bool col_ok = c0 < (hs >> 1);
+      float o8[4][8];
 #pragma unroll
-    for (int r = 0; r < ATT_R; ++r)
-      if (j0 + r < Lk) {
+      for (int r = 0; r < 4; ++r)
+#pragma unroll
+        for (int c = 0; c < 8; ++c) o8[r][c] = 0.f;
+      if (col_ok) pv_tile4<CG>(Pw, Ds, Lq, RS, c0, c1, ig, o8);       // dV = P^T dO
+      pv_reduce_store4<CG>(o8, gvb, P.dv_sl, j0, Lk, c0, c1, ig == 0 && col_ok);
+#pragma unroll
+      for (int r = 0; r < 4; ++r)
+#pragma unroll
+        for (int c = 0; c < 8; ++c) o8[r][c] = 0.f;
+      if (col_ok) pv_tile4<CG>(Sw, Qs, Lq, RS, c0, c1, ig, o8);       // dK = dS^T Q
+      pv_reduce_store4<CG>(o8, gkb, P.dk_sl, j0, Lk, c0, c1, ig == 0 && col_ok);
+    } else {
+      float gk[ATT_R][4], gv[ATT_R][4];
+#pragma unroll
+      for (int r = 0; r < ATT_R; ++r)
+#pragma unroll
+        for (int t = 0; t < 4; ++t) gk[r][t] = gv[r][t] = 0.f;
+      for (int i = 0; i < Lq; ++i) {
+        const float4 p = *reinterpret_cast<const float4*>(Pw + i * ATT_R);
+        const float4 ds = *reinterpret_cast<const float4*>(Sw + i * ATT_R);
 #pragma unroll
         for (int t = 0; t < 4; ++t) {
           const int c = lane + 32 * t;
           if (t < CT && c < hs) {
-            gkb[(long long)(j0 + r) * P.dk_sl + c] = gk[r][t];
-            gvb[(long long)(j0 + r) * P.dv_sl + c] = gv[r][t];
+            const float qq = Qs[i * RS + c], gg = Ds[i * RS + c];
+            gv[0][t] = fmaf(p.x, gg, gv[0][t]);
+            gv[1][t] = fmaf(p.y, gg, gv[1][t]);
+            gv[2][t] = fmaf(p.z, gg, gv[2][t]);
+            gv[3][t] = fmaf(p.w, gg, gv[3][t]);
+            gk[0][t] = fmaf(ds.x, qq, gk[0][t]);
+            gk[1][t] = fmaf(ds.y, qq, gk[1][t]);
+            gk[2][t] = fmaf(ds.z, qq, gk[2][t]);
+            gk[3][t] = fmaf(ds.w, qq, gk[3][t]);
           }
         }
       }
+#pragma unroll
+      for (int r = 0; r < ATT_R; ++r)
+        if (j0 + r < Lk) {
+#pragma unroll
+          for (int t = 0; t < 4; ++t) {
+            const int c = lane + 32 * t;
+            if (t < CT && c < hs) {
+              gkb[(long long)(j0 + r) * P.dk_sl + c] = gk[r][t];
+              gvb[(long long)(j0 + r) * P.dv_sl + c] = gv[r][t];
+            }
+          }
+        }
+    }
     __syncwarp();
   }
 }
@@ -700,10 +780,18 @@ extern "C" int rtf_attn_bwd(const float* d_q, int64_t q_sb, int64_t q_sl, const 
     const int warps = ATT_DQ_THREADS / 32;
     const size_t smem = ((size_t)2 * Lk * RS + (size_t)warps * (2 * ATT_R * hs + Lk * ATT_R)) * 4;
     const int kpl = (Lk + 31) / 32;
-    if (kpl <= 1) rc = attn_launch(attn_bwd_dq_kernel<1>, P, smem, warps * 32, st);
-    else if (kpl <= 2) rc = attn_launch(attn_bwd_dq_kernel<2>, P, smem, warps * 32, st);
-    else if (kpl <= 4) rc = attn_launch(attn_bwd_dq_kernel<4>, P, smem, warps * 32, st);
-    else rc = attn_launch(attn_bwd_dq_kernel<8>, P, smem, warps * 32, st);
+    // 4 x 8 lane tiles for the P.V-shaped products when the head is wide enough (see pv_tile4)
+    const int cgn = (hs % 8 == 0 && hs >= 32) ? (hs <= 32 ? 4 : hs <= 64 ? 8 : 16) : 0;
+#define RTF_DQ(K)                                                                            \
+  (cgn == 0 ? attn_launch(attn_bwd_dq_kernel<K, 0>, P, smem, warps * 32, st)                 \
+   : cgn == 4 ? attn_launch(attn_bwd_dq_kernel<K, 4>, P, smem, warps * 32, st)               \
+   : cgn == 8 ? attn_launch(attn_bwd_dq_kernel<K, 8>, P, smem, warps * 32, st)               \
+              : attn_launch(attn_bwd_dq_kernel<K, 16>, P, smem, warps * 32, st))
+    if (kpl <= 1) rc = RTF_DQ(1);
+    else if (kpl <= 2) rc = RTF_DQ(2);
+    else if (kpl <= 4) rc = RTF_DQ(4);
+    else rc = RTF_DQ(8);
+#undef RTF_DQ
     if (rc) return rc;
   }
   {
@@ -714,10 +802,17 @@ extern "C" int rtf_attn_bwd(const float* d_q, int64_t q_sb, int64_t q_sl, const 
     while (warps > 4 && smem_for(warps) > 227 * 1024) warps -= 2;
     const size_t smem = smem_for(warps);
     const int qpl = (Lq + 31) / 32;
-    if (qpl <= 1) rc = attn_launch(attn_bwd_dkv_kernel<1>, P, smem, warps * 32, st);
-    else if (qpl <= 2) rc = attn_launch(attn_bwd_dkv_kernel<2>, P, smem, warps * 32, st);
-    else if (qpl <= 4) rc = attn_launch(attn_bwd_dkv_kernel<4>, P, smem, warps * 32, st);
-    else rc = attn_launch(attn_bwd_dkv_kernel<8>, P, smem, warps * 32, st);
+    const int cgn = (hs % 8 == 0 && hs >= 32) ? (hs <= 32 ? 4 : hs <= 64 ? 8 : 16) : 0;
+#define RTF_DKV(K)                                                                           \
+  (cgn == 0 ? attn_launch(attn_bwd_dkv_kernel<K, 0>, P, smem, warps * 32, st)                \
+   : cgn == 4 ? attn_launch(attn_bwd_dkv_kernel<K, 4>, P, smem, warps * 32, st)              \
+   : cgn == 8 ? attn_launch(attn_bwd_dkv_kernel<K, 8>, P, smem, warps * 32, st)              \
+              : attn_launch(attn_bwd_dkv_kernel<K, 16>, P, smem, warps * 32, st))
+    if (qpl <= 1) rc = RTF_DKV(1);
+    else if (qpl <= 2) rc = RTF_DKV(2);
+    else if (qpl <= 4) rc = RTF_DKV(4);
+    else rc = RTF_DKV(8);
+#undef RTF_DKV
   }
   return rc;
 }
