@@ -22,12 +22,12 @@
 namespace rtf {
 
 constexpr int ATT_R = 4;          // query rows (or key rows in dkv) per warp step
-// warps per CTA, chosen per kernel from its register need (ptxas: fwd 96, dq 228, dkv 159
+// warps per CTA, chosen per kernel from its register need (ptxas: fwd 96, dq 159, dkv 155
 // registers at 8 keys per lane): one CTA owns a (sample, head) and its K/V (or Q/dO) tiles fill
 // most of the shared memory, so resident warps per SM = warps per CTA — the kernels are bound by
 // shared-memory / FMA latency, and more warps is what hides it.
 constexpr int ATT_FWD_THREADS = 512;
-constexpr int ATT_DQ_THREADS = 256;
+constexpr int ATT_DQ_THREADS = 384;
 constexpr int ATT_DKV_THREADS = 384;
 
 struct AttnParams {
@@ -777,8 +777,12 @@ extern "C" int rtf_attn_bwd(const float* d_q, int64_t q_sb, int64_t q_sl, const 
   const int RS = hs + 4;
   cudaStream_t st = (cudaStream_t)stream;
   {
-    const int warps = ATT_DQ_THREADS / 32;
-    const size_t smem = ((size_t)2 * Lk * RS + (size_t)warps * (2 * ATT_R * hs + Lk * ATT_R)) * 4;
+    int warps = ATT_DQ_THREADS / 32;
+    auto smem_for = [&](int w) {
+      return ((size_t)2 * Lk * RS + (size_t)w * (2 * ATT_R * hs + Lk * ATT_R)) * 4;
+    };
+    while (warps > 4 && smem_for(warps) > 227 * 1024) warps -= 2;
+    const size_t smem = smem_for(warps);
     const int kpl = (Lk + 31) / 32;
     // 4 x 8 lane tiles for the P.V-shaped products when the head is wide enough (see pv_tile4)
     const int cgn = (hs % 8 == 0 && hs >= 32) ? (hs <= 32 ? 4 : hs <= 64 ? 8 : 16) : 0;
