@@ -339,6 +339,17 @@ int rtf_relu_bwd_colsum_workspace(int64_t B, int cols, size_t* bytes);
 int rtf_relu_bwd_colsum(const float* d_gy, const float* d_y, int64_t B, int cols, float* d_g,
                         float* d_colsum, void* d_ws, void* stream);
 
+/* ---- Keras binary_crossentropy on probabilities (the loss of every CTR script) --------------
+ * replaces: model.compile(loss=binary_crossentropy, ...) — src/ctr/fm/train.py:49,
+ *           src/ctr/deep_fm/train.py:50, src/ctr/din/train.py:103 (semantics SURVEY App. A11):
+ *           pc = clip(p, 1e-7, 1-1e-7); loss = -mean(y log(pc+1e-7) + (1-y) log(1-pc+1e-7)).
+ * d_y, d_p: (n) fp32.  d_loss: one float.  d_dp (n) or NULL: d loss / d p (0 where the clip
+ * saturates).  One pass + a one-warp ordered sum of the 1024-element chunk partials
+ * (reproducible) instead of ~30 framework elementwise launches forward + backward.          */
+int rtf_bce_workspace(int64_t n, size_t* bytes);
+int rtf_bce_fwd(const float* d_y, const float* d_p, int64_t n, float* d_loss, float* d_dp,
+                void* d_ws, void* stream);
+
 /* ---- BatchNormalization of the DNN block (MLP either side of the path) -------
  * replaces: tensorflow.keras.layers.BatchNormalization in training mode at the head of
  *           ctr.layers.modules.DNN (src/ctr/layers/modules.py:129-135; Keras defaults App. A9)

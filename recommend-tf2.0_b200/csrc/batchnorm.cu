@@ -147,29 +147,30 @@ bn_reduce_stage1(const float* __restrict__ x, long long ldx, const float* __rest
   }
 }
 
-// Stage 2: 32 columns per CTA, 8 warps; warp w adds chunks w, w + 8, ... of its column in double,
-// the 8 sums are then added in warp order (a fixed tree: reproducible, and 8x less serial than
-// one thread walking the up-to-1024 chunks of a column — 80 us for a 13-column input).
+// Stage 2: 32 columns per CTA, 32 warps; warp w adds chunks w, w + 32, ... of its column in double
+// (ascending, 16 loads in flight), the warps' sums are then added in warp order — a fixed tree:
+// reproducible.  (8 warps with 8 loads in flight took 12-20 us on 432-591 chunks: load latency.)
+constexpr int BN2_WARPS = 32;
 __device__ __forceinline__ void bn_stage2_sums(const float* __restrict__ partial, int chunks, int C,
                                                int c, double (*red)[2][32], double& s0, double& s1) {
   const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
   double a0 = 0.0, a1 = 0.0;
   if (c < C) {
     int k = w;
-    for (; k + 24 < chunks; k += 32) {       // 8 independent loads in flight
-      float t0[4], t1[4];
+    for (; k + 7 * BN2_WARPS < chunks; k += 8 * BN2_WARPS) {   // 16 independent loads in flight
+      float t0[8], t1[8];
 #pragma unroll
-      for (int u = 0; u < 4; ++u) {
-        t0[u] = partial[(long long)(k + 8 * u) * 2 * C + c];
-        t1[u] = partial[(long long)(k + 8 * u) * 2 * C + C + c];
+      for (int u = 0; u < 8; ++u) {
+        t0[u] = partial[(long long)(k + BN2_WARPS * u) * 2 * C + c];
+        t1[u] = partial[(long long)(k + BN2_WARPS * u) * 2 * C + C + c];
       }
 #pragma unroll
-      for (int u = 0; u < 4; ++u) {
+      for (int u = 0; u < 8; ++u) {
         a0 += (double)t0[u];
         a1 += (double)t1[u];
       }
     }
-    for (; k < chunks; k += 8) {
+    for (; k < chunks; k += BN2_WARPS) {
       a0 += (double)partial[(long long)k * 2 * C + c];
       a1 += (double)partial[(long long)k * 2 * C + C + c];
     }
@@ -180,19 +181,19 @@ __device__ __forceinline__ void bn_stage2_sums(const float* __restrict__ partial
   s0 = red[0][0][lane];
   s1 = red[0][1][lane];
 #pragma unroll
-  for (int g = 1; g < 8; ++g) {
+  for (int g = 1; g < BN2_WARPS; ++g) {
     s0 += red[g][0][lane];
     s1 += red[g][1][lane];
   }
 }
 
 // forward stage 2: chunk partials -> mean, invstd (and the Keras moving statistics)
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(BN2_WARPS * 32)
 bn_stats_stage2(const float* __restrict__ partial, int chunks, const float* __restrict__ x,
                 long long B, int C, float eps, float momentum, float* __restrict__ mean,
                 float* __restrict__ invstd, float* __restrict__ moving_mean,
                 float* __restrict__ moving_var) {
-  __shared__ double red[8][2][32];
+  __shared__ double red[BN2_WARPS][2][32];
   const int c = blockIdx.x * 32 + (threadIdx.x & 31);
   double s0, s1;
   bn_stage2_sums(partial, chunks, C, c, red, s0, s1);
@@ -210,11 +211,11 @@ bn_stats_stage2(const float* __restrict__ partial, int chunks, const float* __re
 }
 
 // backward stage 2: -> sum dy (= dbeta), sum dy (x - mean), dgamma
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(BN2_WARPS * 32)
 bn_bwd_stage2(const float* __restrict__ partial, int chunks, int C, const float* __restrict__ invstd,
               float* __restrict__ sum_dy, float* __restrict__ sum_dy_xmu, float* __restrict__ dgamma,
               float* __restrict__ dbeta) {
-  __shared__ double red[8][2][32];
+  __shared__ double red[BN2_WARPS][2][32];
   const int c = blockIdx.x * 32 + (threadIdx.x & 31);
   double s0, s1;
   bn_stage2_sums(partial, chunks, C, c, red, s0, s1);
@@ -339,7 +340,7 @@ extern "C" int rtf_bn_fwd(const float* d_x, int64_t ldx, int64_t B, int C, const
   else
     bn_reduce_stage1<1, 0><<<g, BN_THREADS, 0, st>>>(d_x, ldx, nullptr, 0, nullptr, B, C, t.cx, t.ry,
                                                      t.rows_per_chunk, partial);
-  bn_stats_stage2<<<(C + 31) / 32, 256, 0, st>>>(partial, t.chunks, d_x, B, C, eps, momentum, d_mean,
+  bn_stats_stage2<<<(C + 31) / 32, BN2_WARPS * 32, 0, st>>>(partial, t.chunks, d_x, B, C, eps, momentum, d_mean,
                                                    d_invstd, d_moving_mean, d_moving_var);
   if (d_y) {
     if (bn_vec4(C, {ldx, ldy}, {d_x, d_y, d_mean, d_invstd, d_gamma, d_beta}))
@@ -379,7 +380,7 @@ extern "C" int rtf_bn_bwd(const float* d_dy, int64_t lddy, const float* d_x, int
   else
     bn_reduce_stage1<1, 1><<<g, BN_THREADS, 0, st>>>(d_x, ldx, d_dy, lddy, d_mean, B, C, t.cx, t.ry,
                                                      t.rows_per_chunk, partial);
-  bn_bwd_stage2<<<(C + 31) / 32, 256, 0, st>>>(partial, t.chunks, C, d_invstd, sum_dy, sum_dy_xmu,
+  bn_bwd_stage2<<<(C + 31) / 32, BN2_WARPS * 32, 0, st>>>(partial, t.chunks, C, d_invstd, sum_dy, sum_dy_xmu,
                                                  d_dgamma, d_dbeta);
   if (d_dx) {
     if (bn_vec4(C, {ldx, lddy, lddx}, {d_x, d_dy, d_dx, d_mean, d_invstd, d_gamma, d_ws}))

@@ -41,33 +41,35 @@ relu_bwd_colsum_stage1(const float* __restrict__ gy, const float* __restrict__ y
   *reinterpret_cast<float4*>(partial + ((long long)blockIdx.y * ny + ty) * Ccols + c4) = acc;
 }
 
-// 32 columns per CTA, 8 warps: warp g adds chunks g, g+8, g+16, ... (ascending), the 8 partial
-// sums are then added in warp order — a fixed tree, so the result is reproducible, and 8x less
-// serial than one thread walking all chunks of a column.
-__global__ void __launch_bounds__(256)
+// 32 columns per CTA, 32 warps: warp g adds chunks g, g+32, g+64, ... (ascending) with 16 loads in
+// flight, the 32 partial sums are then added in warp order — a fixed tree, so the result is
+// reproducible.  (8 warps x 4 loads in flight took 11-39 us per layer on 512-2048 partial rows:
+// pure load latency, 0.125 ms of the DLRM step.)
+constexpr int RB2_WARPS = 32, RB2_UNROLL = 16;
+__global__ void __launch_bounds__(RB2_WARPS * 32)
 relu_bwd_colsum_stage2(const float* __restrict__ partial, int nchunks, int Ccols,
                        float* __restrict__ out) {
-  __shared__ float part[8][32];
+  __shared__ float part[RB2_WARPS][33];
   const int lane = threadIdx.x & 31, grp = threadIdx.x >> 5;
   const int c = blockIdx.x * 32 + lane;
   float acc = 0.f;
   if (c < Ccols) {
     int k = grp;
-    for (; k + 24 < nchunks; k += 32) {   // 4 independent loads in flight
-      const float a0 = partial[(long long)k * Ccols + c];
-      const float a1 = partial[(long long)(k + 8) * Ccols + c];
-      const float a2 = partial[(long long)(k + 16) * Ccols + c];
-      const float a3 = partial[(long long)(k + 24) * Ccols + c];
-      acc = __fadd_rn(__fadd_rn(__fadd_rn(__fadd_rn(acc, a0), a1), a2), a3);
+    for (; k + (RB2_UNROLL - 1) * RB2_WARPS < nchunks; k += RB2_UNROLL * RB2_WARPS) {
+      float a[RB2_UNROLL];
+#pragma unroll
+      for (int u = 0; u < RB2_UNROLL; ++u) a[u] = partial[(long long)(k + u * RB2_WARPS) * Ccols + c];
+#pragma unroll
+      for (int u = 0; u < RB2_UNROLL; ++u) acc = __fadd_rn(acc, a[u]);
     }
-    for (; k < nchunks; k += 8) acc = __fadd_rn(acc, partial[(long long)k * Ccols + c]);
+    for (; k < nchunks; k += RB2_WARPS) acc = __fadd_rn(acc, partial[(long long)k * Ccols + c]);
   }
   part[grp][lane] = acc;
   __syncthreads();
   if (grp == 0 && c < Ccols) {
     float t = part[0][lane];
 #pragma unroll
-    for (int g = 1; g < 8; ++g) t = __fadd_rn(t, part[g][lane]);
+    for (int g = 1; g < RB2_WARPS; ++g) t = __fadd_rn(t, part[g][lane]);
     out[c] = t;
   }
 }
@@ -110,7 +112,7 @@ extern "C" int rtf_relu_bwd_colsum(const float* d_gy, const float* d_y, int64_t 
   const int lx = relu_bwd_lx(cols), ny = 128 / lx;
   dim3 g1((cols / 4 + lx - 1) / lx, nchunks);
   relu_bwd_colsum_stage1<<<g1, 128, 0, st>>>(d_gy, d_y, B, cols, lx, rb, d_g, (float*)d_ws);
-  relu_bwd_colsum_stage2<<<(cols + 31) / 32, 256, 0, st>>>((const float*)d_ws, nchunks * ny, cols,
+  relu_bwd_colsum_stage2<<<(cols + 31) / 32, RB2_WARPS * 32, 0, st>>>((const float*)d_ws, nchunks * ny, cols,
                                                            d_colsum);
   RTF_CHECK_LAUNCH();
   return 0;
