@@ -110,6 +110,40 @@ __device__ __forceinline__ void dot_issue_rows(const DotParams& P, long long b, 
   }
 }
 
+// The same in two steps: ids -> row sources of sample b (lane owns rows lane and lane + 32) without
+// touching shared memory, then the copies.  A warp resolves the NEXT sample's addresses (a dependent
+// global load, ~1 us) before its FMA loop and issues the copies the moment the tile is free, instead
+// of paying the id load in front of every gather.
+template <typename IdT>
+__device__ __forceinline__ void dot_resolve_rows(const DotParams& P, long long b, int lane,
+                                                 const float* (&src)[2]) {
+#pragma unroll
+  for (int k = 0; k < 2; ++k) {
+    const int r = lane + 32 * k;
+    src[k] = r < P.F1 ? dot_src_row<IdT>(P, b, r) : nullptr;
+  }
+}
+__device__ __forceinline__ void dot_issue_resolved(const DotParams& P, float* xt, int RS,
+                                                   uint64_t* bar, int lane,
+                                                   const float* const (&src)[2]) {
+  const int F1 = P.F1, D = P.D;
+  unsigned nvalid = 0;
+#pragma unroll
+  for (int k = 0; k < 2; ++k) {
+    const int r = lane + 32 * k;
+    if (r < F1 && !src[k])
+      for (int d = 0; d < D; ++d) xt[r * RS + d] = 0.f;  // bad id: row reads as zeros
+    nvalid += __popc(__ballot_sync(0xffffffffu, src[k] != nullptr));
+  }
+  if (lane == 0) mbar_expect_tx(bar, nvalid * (unsigned)D * 4u);
+  __syncwarp();
+#pragma unroll
+  for (int k = 0; k < 2; ++k) {
+    const int r = lane + 32 * k;
+    if (src[k]) bulk_g2s(xt + r * RS, src[k], (unsigned)D * 4u, bar);
+  }
+}
+
 __device__ __forceinline__ void tri_block(int blk, int& bi, int& bj) {
   // blk -> (bi, bj), bj <= bi, row-major over the lower triangle of blocks
   int i = (int)((sqrtf(8.f * blk + 1.f) - 1.f) * 0.5f);
@@ -274,6 +308,9 @@ dot_fwd7_kernel(const __grid_constant__ DotParams P, int warp_floats) {
   for (; b < P.B; b += stride) {
     if (!(P.dbg & 2)) mbar_wait(bar, parity);
     parity ^= 1;
+    const bool more = b + stride < P.B && !(P.dbg & 2);
+    const float* src[2] = {nullptr, nullptr};
+    if (more) dot_resolve_rows<IdT>(P, b + stride, lane, src);   // id loads fly under the Gram loop
     float2 acc[7][7];
 #pragma unroll
     for (int r = 0; r < 7; ++r)
@@ -309,7 +346,7 @@ dot_fwd7_kernel(const __grid_constant__ DotParams P, int warp_floats) {
       }
     }
     __syncwarp();  // every lane is done reading xt
-    if (b + stride < P.B && !(P.dbg & 2)) dot_issue_rows<IdT>(P, b + stride, xt, RS, bar, lane);
+    if (more) dot_issue_resolved(P, xt, RS, bar, lane, src);
     // d-group partials -> group 0, added in group order
     float z[7][7];
 #pragma unroll
@@ -551,7 +588,12 @@ dot_bwd_kernel(const __grid_constant__ DotParams P, int warp_floats) {
       }
     }
     const float4 g0 = g0pre;
-    if (b + stride < P.B) prefetch(b + stride);
+    const bool more = b + stride < P.B;
+    const float* src[2] = {nullptr, nullptr};
+    if (more) {
+      prefetch(b + stride);
+      if (!(P.dbg & 2)) dot_resolve_rows<IdT>(P, b + stride, lane, src);  // id loads fly under the FMA loop
+    }
     __syncwarp();
     if (!(P.dbg & 2)) mbar_wait(bar, parity);
     parity ^= 1;
@@ -625,7 +667,7 @@ dot_bwd_kernel(const __grid_constant__ DotParams P, int warp_floats) {
       }
     }
     __syncwarp();
-    if (b + stride < P.B && !(P.dbg & 2)) dot_issue_rows<IdT>(P, b + stride, xt, RS, bar, lane);
+    if (more && !(P.dbg & 2)) dot_issue_resolved(P, xt, RS, bar, lane, src);
   }
 }
 
