@@ -506,12 +506,21 @@ dot_fwd_kernel_v2(const __grid_constant__ DotParams P, int warp_floats, int cta_
 #endif  // RTF_DOT_EXPERIMENTS
 
 // backward: dX[i] = sum_j S[i][j] X[j],  S symmetric from dZ, plus the passthrough on row 0
-template <typename IdT>
+// row pairs of the t-th 8-row tile of an F1-row sample (the last tile only the pairs that exist)
+__host__ __device__ constexpr int bwd_tile_rpn(int f1, int t) {
+  return (f1 - 8 * t) > 6 ? 4 : (f1 - 8 * t) > 4 ? 3 : (f1 - 8 * t) > 2 ? 2 : 1;
+}
+
+// CF1 / CD: compile-time row count and embedding width (0 = runtime).  The kernel issues ~4 000
+// instructions per sample of which 1 512 are FFMA2 (ncu: issue slots 50 %, nothing else near a
+// limit), so for the shape the bench and the reference's Criteo DLRM use the loop bounds, shared-
+// memory strides and tile dispatch are constants: the j loops unroll fully onto immediate offsets.
+template <typename IdT, int CF1 = 0, int CD = 0>
 __global__ void __launch_bounds__(512, 1)
 dot_bwd_kernel(const __grid_constant__ DotParams P, int warp_floats) {
   extern __shared__ __align__(16) float smem[];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
-  const int F1 = P.F1, D = P.D;
+  const int F1 = CF1 ? CF1 : P.F1, D = CD ? CD : P.D;
   const int F1p = (F1 + 7) & ~7;  // i-tiles of 8 rows
   const int SS = F1p + 4;         // S row stride: the mirrored writes S[j][i] of consecutive j would
                                   // all hit one bank with a stride of 32
@@ -610,7 +619,7 @@ dot_bwd_kernel(const __grid_constant__ DotParams P, int warp_floats) {
       for (int rp = 0; rp < RPN; ++rp)
 #pragma unroll
         for (int c = 0; c < 4; ++c) acc2[rp][c] = make_float2(0.f, 0.f);
-#pragma unroll 3
+#pragma unroll (CF1 ? CF1 : 3)
       for (int j = 0; j < ((P.dbg & 1) ? 0 : F1); ++j) {
         const float4 xj = *reinterpret_cast<const float4*>(xt + j * RS + d0);
         const float4 s0 = *reinterpret_cast<const float4*>(S + j * SS + i0);
@@ -658,12 +667,21 @@ dot_bwd_kernel(const __grid_constant__ DotParams P, int warp_floats) {
       }
     };
     for (int d0 = lane * 4; d0 < D; d0 += 128) {
-      for (int i0 = 0; i0 < F1; i0 += 8) {
-        const int left = F1 - i0;
-        if (left > 6) tile(std::integral_constant<int, 4>{}, i0, d0);
-        else if (left > 4) tile(std::integral_constant<int, 3>{}, i0, d0);
-        else if (left > 2) tile(std::integral_constant<int, 2>{}, i0, d0);
-        else tile(std::integral_constant<int, 1>{}, i0, d0);
+      if constexpr (CF1 > 0) {     // the tiles and their row-pair counts are known: straight-line code
+        static_assert(CF1 <= 32, "compile-time row count: at most four 8-row tiles");
+        constexpr int NT = (CF1 + 7) / 8;
+        tile(std::integral_constant<int, bwd_tile_rpn(CF1, 0)>{}, 0, d0);
+        if constexpr (NT > 1) tile(std::integral_constant<int, bwd_tile_rpn(CF1, 1)>{}, 8, d0);
+        if constexpr (NT > 2) tile(std::integral_constant<int, bwd_tile_rpn(CF1, 2)>{}, 16, d0);
+        if constexpr (NT > 3) tile(std::integral_constant<int, bwd_tile_rpn(CF1, 3)>{}, 24, d0);
+      } else {
+        for (int i0 = 0; i0 < F1; i0 += 8) {
+          const int left = F1 - i0;
+          if (left > 6) tile(std::integral_constant<int, 4>{}, i0, d0);
+          else if (left > 4) tile(std::integral_constant<int, 3>{}, i0, d0);
+          else if (left > 2) tile(std::integral_constant<int, 2>{}, i0, d0);
+          else tile(std::integral_constant<int, 1>{}, i0, d0);
+        }
       }
     }
     __syncwarp();
@@ -1011,6 +1029,10 @@ static int dot_bwd_impl(DotParams& P, int ids_i64, cudaStream_t st) {
 #endif
   const int warp_floats = P.F1 * RS + P.F1 * (F1p + 4) + 4 + 128;  // + mbarrier slot + 64 ids
   const int cta_floats = ((npairs + 1) / 2 + 3) & ~3;
+  static const int variant = getenv("RTF_DOT_BWD") ? atoi(getenv("RTF_DOT_BWD")) : 1;
+  if (variant == 1 && P.F1 == 27 && P.D == 128)    // the Criteo shape (26 tables + the dense row)
+    return ids_i64 ? dot_launch(dot_bwd_kernel<int64_t, 27, 128>, P, warp_floats, cta_floats, st)
+                   : dot_launch(dot_bwd_kernel<int32_t, 27, 128>, P, warp_floats, cta_floats, st);
   return ids_i64 ? dot_launch(dot_bwd_kernel<int64_t>, P, warp_floats, cta_floats, st)
                  : dot_launch(dot_bwd_kernel<int32_t>, P, warp_floats, cta_floats, st);
 }
