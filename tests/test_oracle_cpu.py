@@ -52,3 +52,26 @@ def test_adam_matches_closed_form_first_step():
 def test_out_of_range_ids_get_sentinel_key():
     keys, rb = O.make_keys(np.array([[[1], [9]]]), [0, 1], [4, 4])
     assert keys[0] == 1 and keys[1] == (2 << rb)
+
+
+def test_binary_crossentropy_host_path_matches_oracle_and_loop_restatement():
+    """Keras binary_crossentropy (App. A11, src/ctr/fm/train.py:49): the package's CPU-tensor path
+    (framework ops; CUDA tensors take rtf_bce_fwd, tests/test_loss_gpu.py), the oracle's
+    restatement and a plain-Python loop over the formula agree."""
+    import math
+    import torch
+    import recommend_tf2_b200 as pkg
+    from oracle.dlrm_ref import bce
+    g = torch.Generator().manual_seed(11)
+    p = torch.rand(257, 1, generator=g, dtype=torch.float64)
+    p[0], p[1], p[2] = 0.0, 1.0, 1e-9
+    y = (torch.rand(257, generator=g) < 0.4).double()
+    got = pkg.layers.binary_crossentropy(y, p)
+    want = bce(y.reshape(p.shape), p)
+    eps = 1e-7
+    acc = 0.0
+    for yi, pi in zip(y.tolist(), p.reshape(-1).tolist()):
+        pc = min(max(pi, eps), 1 - eps)
+        acc += yi * math.log(pc + eps) + (1 - yi) * math.log(1 - pc + eps)
+    assert abs(float(got) - float(want)) < 1e-12
+    assert abs(float(got) + acc / 257) < 1e-12
