@@ -576,7 +576,15 @@ autoint_dw_reduce(const float* __restrict__ partial, int ncta, int n, float* __r
   const int e = blockIdx.x * blockDim.x + threadIdx.x;
   if (e >= n) return;
   float acc = 0.f;
-  for (int c = 0; c < ncta; ++c) acc = __fadd_rn(acc, partial[(long long)c * n + e]);
+  int c = 0;
+  for (; c + 16 <= ncta; c += 16) {     // 16 loads in flight, added in the same (ascending) order
+    float t[16];
+#pragma unroll
+    for (int u = 0; u < 16; ++u) t[u] = partial[(long long)(c + u) * n + e];
+#pragma unroll
+    for (int u = 0; u < 16; ++u) acc = __fadd_rn(acc, t[u]);
+  }
+  for (; c < ncta; ++c) acc = __fadd_rn(acc, partial[(long long)c * n + e]);
   gW[e] = acc;
 }
 

@@ -132,31 +132,33 @@ ln_bwd_kernel(const float* __restrict__ dy, const float* __restrict__ x, const f
   }
 }
 
-// chunk partials -> dgamma, dbeta: 32 columns per CTA, warp w adds chunks w, w+8, ... in double,
-// the 8 sums are added in warp order
-__global__ void __launch_bounds__(256)
+// chunk partials -> dgamma, dbeta: 32 columns per CTA, 32 warps; warp w adds chunks w, w+32, ... in
+// double (ascending, 16 loads in flight), the warps' sums are added in warp order: a fixed tree
+// (8 warps with 8 loads in flight took 15 us per call: load latency)
+constexpr int LN2_WARPS = 32;
+__global__ void __launch_bounds__(LN2_WARPS * 32)
 ln_bwd_stage2(const float* __restrict__ partial, long long chunks, int C, float* __restrict__ dgamma,
               float* __restrict__ dbeta) {
-  __shared__ double red[8][2][32];
+  __shared__ double red[LN2_WARPS][2][32];
   const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
   const int c = blockIdx.x * 32 + lane;
   double a0 = 0.0, a1 = 0.0;
   if (c < C) {
     long long k = w;
-    for (; k + 24 < chunks; k += 32) {
-      float t0[4], t1[4];
+    for (; k + 7 * LN2_WARPS < chunks; k += 8 * LN2_WARPS) {
+      float t0[8], t1[8];
 #pragma unroll
-      for (int u = 0; u < 4; ++u) {
-        t0[u] = partial[(k + 8 * u) * 2 * C + c];
-        t1[u] = partial[(k + 8 * u) * 2 * C + C + c];
+      for (int u = 0; u < 8; ++u) {
+        t0[u] = partial[(k + LN2_WARPS * u) * 2 * C + c];
+        t1[u] = partial[(k + LN2_WARPS * u) * 2 * C + C + c];
       }
 #pragma unroll
-      for (int u = 0; u < 4; ++u) {
+      for (int u = 0; u < 8; ++u) {
         a0 += (double)t0[u];
         a1 += (double)t1[u];
       }
     }
-    for (; k < chunks; k += 8) {
+    for (; k < chunks; k += LN2_WARPS) {
       a0 += (double)partial[k * 2 * C + c];
       a1 += (double)partial[k * 2 * C + C + c];
     }
@@ -167,7 +169,7 @@ ln_bwd_stage2(const float* __restrict__ partial, long long chunks, int C, float*
   if (w == 0 && c < C) {
     double s0 = red[0][0][lane], s1 = red[0][1][lane];
 #pragma unroll
-    for (int g = 1; g < 8; ++g) {
+    for (int g = 1; g < LN2_WARPS; ++g) {
       s0 += red[g][0][lane];
       s1 += red[g][1][lane];
     }
@@ -247,7 +249,7 @@ extern "C" int rtf_layernorm_bwd(const float* d_dy, const float* d_x, const floa
   else RTF_LN_BWD(8);
 #undef RTF_LN_BWD
   if (d_dgamma || d_dbeta)
-    ln_bwd_stage2<<<(C + 31) / 32, 256, 0, st>>>((const float*)d_ws, chunks, C, d_dgamma, d_dbeta);
+    ln_bwd_stage2<<<(C + 31) / 32, LN2_WARPS * 32, 0, st>>>((const float*)d_ws, chunks, C, d_dgamma, d_dbeta);
   RTF_CHECK_LAUNCH();
   return 0;
 }
