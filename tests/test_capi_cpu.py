@@ -67,3 +67,31 @@ def test_product_package_never_imports_oracle():
             if fn.endswith((".py", ".cu", ".cuh", ".h")):
                 txt = open(os.path.join(dp, fn)).read()
                 assert "import oracle" not in txt and "from oracle" not in txt, fn
+
+
+def test_tf_shim_source_type_checks_against_the_c_header(tmp_path):
+    """tf_ops/rtf_tf_ops.cc (the tf.load_op_library shim) cannot be built here (no
+    TensorFlow headers).  It is TYPE-CHECKED instead against a declaration-only stand-in for the
+    TensorFlow names it uses (tests/tf_stub, test infrastructure) and the REAL include/rtf_b200.h:
+    every call into librtf_b200 must match the C-ABI in argument count and types; a deliberately
+    broken call must be rejected (the check has teeth)."""
+    import shutil
+    import subprocess
+    gxx = shutil.which("g++")
+    if gxx is None:
+        pytest.skip("no g++")
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    src = os.path.join(root, "tf_ops", "rtf_tf_ops.cc")
+    cmd = [gxx, "-std=c++17", "-fsyntax-only", "-I" + os.path.join(root, "tests", "tf_stub"),
+           "-I" + os.path.join(root, "include")]
+    ok = subprocess.run(cmd + [src], capture_output=True, text=True)
+    assert ok.returncode == 0, ok.stderr[-2000:]
+    text = open(src).read()
+    for name in ("RtfEmbedFwd", "RtfEmbedBwdAdam", "RtfEmbedDotFwd", "RtfEmbedDotBwd", "RtfBce"):
+        assert f'REGISTER_OP("{name}")' in text and f'Name("{name}")' in text
+    broken = tmp_path / "broken.cc"
+    needle = "ws.flat<uint8>().data(), StreamOf(ctx));"
+    assert needle in text
+    broken.write_text(text.replace(needle, "StreamOf(ctx));"))      # one argument short
+    bad = subprocess.run(cmd + [str(broken)], capture_output=True, text=True)
+    assert bad.returncode != 0 and "rtf_bce_fwd" in bad.stderr

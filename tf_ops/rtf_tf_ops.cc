@@ -11,6 +11,8 @@
 //                                                          src/ctr/fm/train.py:49-50
 //   RtfEmbedDotFwd / RtfEmbedDotBwd   K1+K4  gather + DLRM pairwise dot (src/ctr/dlrm/model.py:48,
 //                                     defined from the paper cited at :7)
+//   RtfBce           Keras binary_crossentropy on probabilities + d loss / d p in one pass
+//                                                          src/ctr/fm/train.py:49
 // The remaining entry points of include/rtf_b200.h wrap the same way.
 #include <cstdint>
 #include <vector>
@@ -248,3 +250,38 @@ class RtfEmbedDotBwdOp : public OpKernel {
   }
 };
 REGISTER_KERNEL_BUILDER(Name("RtfEmbedDotBwd").Device(DEVICE_GPU), RtfEmbedDotBwdOp);
+
+// ----------------------------------------------------------------------------- loss
+REGISTER_OP("RtfBce")
+    .Input("y_true: float")   // (n) labels
+    .Input("y_pred: float")   // (n) probabilities
+    .Output("loss: float")    // scalar: -mean(y log(pc + 1e-7) + (1 - y) log(1 - pc + 1e-7))
+    .Output("dp: float")      // (n): d loss / d y_pred (0 where the clip saturates)
+    .SetShapeFn([](InferenceContext* c) {
+      c->set_output(0, c->Scalar());
+      c->set_output(1, c->input(1));
+      return OkStatus();
+    });
+
+class RtfBceOp : public OpKernel {
+ public:
+  explicit RtfBceOp(OpKernelConstruction* c) : OpKernel(c) {}
+  void Compute(OpKernelContext* ctx) override {
+    const Tensor& y = ctx->input(0);
+    const Tensor& p = ctx->input(1);
+    const int64_t n = p.NumElements();
+    OP_REQUIRES(ctx, y.NumElements() == n && n > 0, errors::InvalidArgument("RtfBce: shapes"));
+    Tensor *loss = nullptr, *dp = nullptr;
+    OP_REQUIRES_OK(ctx, ctx->allocate_output(0, {}, &loss));
+    OP_REQUIRES_OK(ctx, ctx->allocate_output(1, p.shape(), &dp));
+    size_t ws_bytes = 0;
+    OP_REQUIRES(ctx, rtf_bce_workspace(n, &ws_bytes) == 0, errors::Internal("rtf_bce_workspace"));
+    Tensor ws;
+    OP_REQUIRES_OK(ctx, ctx->allocate_temp(DT_UINT8, {static_cast<int64_t>(ws_bytes)}, &ws));
+    const int rc = rtf_bce_fwd(y.flat<float>().data(), p.flat<float>().data(), n,
+                               loss->flat<float>().data(), dp->flat<float>().data(),
+                               ws.flat<uint8>().data(), StreamOf(ctx));
+    OP_REQUIRES(ctx, rc == 0, errors::Internal("rtf_bce_fwd rc=", rc));
+  }
+};
+REGISTER_KERNEL_BUILDER(Name("RtfBce").Device(DEVICE_GPU), RtfBceOp);
