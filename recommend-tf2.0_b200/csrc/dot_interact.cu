@@ -516,7 +516,7 @@ __host__ __device__ constexpr int bwd_tile_rpn(int f1, int t) {
 // limit), so for the shape the bench and the reference's Criteo DLRM use the loop bounds, shared-
 // memory strides and tile dispatch are constants: the j loops unroll fully onto immediate offsets.
 template <typename IdT, int CF1 = 0, int CD = 0>
-__global__ void __launch_bounds__(512, 1)
+__global__ void __launch_bounds__(CF1 ? 384 : 512, 1)   // the compile-time shape runs 12 warps (shared memory)
 dot_bwd_kernel(const __grid_constant__ DotParams P, int warp_floats) {
   extern __shared__ __align__(16) float smem[];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
@@ -1031,8 +1031,8 @@ static int dot_bwd_impl(DotParams& P, int ids_i64, cudaStream_t st) {
   const int cta_floats = ((npairs + 1) / 2 + 3) & ~3;
   static const int variant = getenv("RTF_DOT_BWD") ? atoi(getenv("RTF_DOT_BWD")) : 1;
   if (variant == 1 && P.F1 == 27 && P.D == 128)    // the Criteo shape (26 tables + the dense row)
-    return ids_i64 ? dot_launch(dot_bwd_kernel<int64_t, 27, 128>, P, warp_floats, cta_floats, st)
-                   : dot_launch(dot_bwd_kernel<int32_t, 27, 128>, P, warp_floats, cta_floats, st);
+    return ids_i64 ? dot_launch(dot_bwd_kernel<int64_t, 27, 128>, P, warp_floats, cta_floats, st, 12)
+                   : dot_launch(dot_bwd_kernel<int32_t, 27, 128>, P, warp_floats, cta_floats, st, 12);
   return ids_i64 ? dot_launch(dot_bwd_kernel<int64_t>, P, warp_floats, cta_floats, st)
                  : dot_launch(dot_bwd_kernel<int32_t>, P, warp_floats, cta_floats, st);
 }
